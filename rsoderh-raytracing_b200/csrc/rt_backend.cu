@@ -1,0 +1,1103 @@
+// rt_backend.cu — kernels and extern "C" surface of librt_backend.so (include/rt_backend.h).
+//
+// Replaces the reference's device/pipeline layer (src/state.rs) and its compute shader
+// (src/shaders/shader.wgsl) with sm_100a CUDA. One thread owns one pixel and walks that
+// pixel's samples in order (accumulator in registers, one 16-byte store per pixel per
+// launch); a lane whose path ends starts its pixel's next sample at once, so warps stay
+// populated although path lengths differ.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "rt_backend.h"
+#include "rt_device.cuh"
+
+using namespace rtd;
+
+// =====================================================================================
+// Kernels
+// =====================================================================================
+
+struct RenderParams {
+    SceneView scene;
+    EnvView env;
+    CameraParams camera;
+    float4* accum;                 // W*H rgba32f
+    unsigned long long* counters;  // RtCounters as 12 x u64
+    uint32_t width, height;
+    uint32_t sample_begin, sample_count;
+    uint32_t max_bounces;
+};
+
+constexpr int kTileW = 16, kTileH = 8, kBlockThreads = kTileW * kTileH;
+
+// Pixel owned by this thread: a warp covers an 8x4 patch, a block a 16x8 tile.
+RT_DEV void thread_pixel(uint32_t& px, uint32_t& py) {
+    uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    px = blockIdx.x * kTileW + (warp & 1u) * 8u + (lane & 7u);
+    py = blockIdx.y * kTileH + (warp >> 1) * 4u + (lane >> 3);
+}
+
+RT_DEV void flush_counts(const Counts& cn, unsigned long long* out, bool detailed) {
+    const uint32_t vals[12] = {cn.paths, cn.rays,    cn.shadow_rays, cn.nodes,  cn.tris,        cn.spheres,
+                               cn.planes, cn.hits,   cn.tri_hits,    cn.shaded, cn.env_lookups, cn.fallback};
+    int n = detailed ? 12 : 3;
+    for (int i = 0; i < n; i++) {
+        uint32_t v = vals[i];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
+        if ((threadIdx.x & 31u) == 0u && v) atomicAdd(out + i, (unsigned long long)v);
+    }
+}
+
+template <bool COUNT, int STACK_CAP>
+__global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParams p) {
+    uint32_t px, py;
+    thread_pixel(px, py);
+    const bool active = px < p.width && py < p.height;
+    const size_t pixel = (size_t)py * p.width + px;
+
+    Counts cn;
+    memset(&cn, 0, sizeof cn);
+    uint32_t stack[STACK_CAP];
+
+    const float sin_half_fov = rt_sin(p.camera.fov_y / 2.0f);
+    const uint32_t sample_end = p.sample_begin + p.sample_count;
+
+    float4 acc4 = active ? p.accum[pixel] : make_float4(0.f, 0.f, 0.f, 0.f);
+    V3 acc = v3(acc4.x, acc4.y, acc4.z);
+
+    uint32_t sample = (active && p.max_bounces > 0u) ? p.sample_begin : sample_end;
+
+    // Path state.
+    uint32_t rng = 0u, bounce = 0u;
+    V3 o = v3s(0.f), d = v3s(0.f), T = v3s(1.f), L = v3s(0.f);
+    float last_pdf = 1.0f;
+    if (sample < sample_end) {
+        camera_ray(p.camera, sin_half_fov, px, py, p.width, p.height, sample, rng, o, d);
+        cn.paths++;
+    }
+
+    while (sample < sample_end) {
+        bool done = false;
+        Hit hit;
+        cn.rays++;
+        cast_ray<COUNT>(p.scene, o, d, hit, stack, cn);
+
+        if (hit.rec == 0xFFFFFFFFu) {
+            // shader.wgsl:1222-1231 — escaped into the environment.
+            float u, v;
+            direction_to_uv(d, u, v);
+            V3 sky = env_bilinear(p.env, u, v);
+            if (COUNT) cn.env_lookups++;
+            float pdf = env_direction_pdf(p.env, u, v);
+            float w = power_heuristic(last_pdf, pdf);
+            L = L + T * sky * w;
+            done = true;
+        } else {
+            V3 point, n;
+            uint32_t mat_id;
+            reconstruct_hit(p.scene, o, d, hit, point, n, mat_id);
+            if (COUNT) {
+                cn.hits++;
+                if (hit.rec < p.scene.slot_count &&
+                    __float_as_int(ld4(p.scene.records + 4u * (size_t)hit.rec).w) == 2)
+                    cn.tri_hits++;
+            }
+            Material m = load_material(p.scene, mat_id);
+            L = L + T * m.emission;  // shader.wgsl:1236
+
+            V3 wo_world = -d;
+            Frame frame = make_frame(n);
+            V3 wo = to_local(frame, wo_world);
+
+            // ---- next-event estimation: sample_environment (shader.wgsl:782-820) ----
+            {
+                if (COUNT) cn.shaded++;
+                uint32_t length = p.env.width * p.env.height;
+                uint32_t index = min((uint32_t)(rng_uniform(rng) * (float)length), length - 1u);
+                float4 entry = ld4(p.env.alias + index);
+                uint32_t pick = rng_uniform(rng) < entry.x ? index : __float_as_uint(entry.y);
+                uint32_t ex = pick % p.env.width, ey = pick / p.env.width;
+                float jx = rng_uniform(rng), jy = rng_uniform(rng);
+                float eu = ((float)ex + jx) / (float)p.env.width;
+                float ev = ((float)ey + jy) / (float)p.env.height;
+                float phi = (2.0f * eu - 1.0f) * RT_PI;
+                float theta = RT_PI * ev;
+                float st, ct, sph, cph;
+                rt_sincos(theta, &st, &ct);
+                rt_sincos(phi, &sph, &cph);
+                V3 wi_world = v3(st * cph, ct, st * sph);
+                float pmf = pick == index ? entry.z : ld4(p.env.alias + pick).z;
+                // environment_pixel_solid_angle (shader.wgsl:739-749); sin(theta) is `st`.
+                float d_phi = RT_TWO_PI / (float)p.env.width;
+                float d_theta = RT_PI / (float)p.env.height;
+                float pdf_env = pmf / (d_phi * d_theta * fmaxf(1.0e-6f, st));
+                float cos_theta = fmaxf(0.0f, dot(n, wi_world));
+                // The reference fetches the radiance unconditionally; it is only consumed
+                // when the sample is unoccluded, so fetch it there.
+                if (COUNT) cn.env_lookups++;
+                if (cos_theta > 0.0f && pdf_env > 0.0f) {
+                    Hit shadow;
+                    cn.shadow_rays++;
+                    traverse<true, COUNT>(p.scene, point, wi_world, shadow, stack, cn);
+                    if (shadow.rec == 0xFFFFFFFFu) {
+                        V3 radiance = env_bilinear(p.env, eu, ev);
+                        V3 wi = to_local(frame, wi_world);
+                        V3 f;
+                        float pdf_bsdf;
+                        bsdf_eval_pdf(wo, wi, m, f, pdf_bsdf);
+                        float w = power_heuristic(pdf_env, pdf_bsdf);
+                        L = L + T * w * radiance * f * cos_theta / pdf_env;
+                    }
+                }
+            }
+
+            // ---- bsdf_sample (shader.wgsl:1116-1202) + path update (1270-1298) ----
+            if (dot(n, wo_world) <= 0.0f) {
+                L = v3(0.f, 0.f, 1.f);
+                done = true;
+            } else if (wo.z <= 0.0f) {
+                L = v3(0.f, 1.f, 0.f);
+                done = true;
+            } else {
+                float sample_u = rng_uniform(rng);
+                V3 wi;
+                bool blocked = false;
+                if (sample_u < m.p_diff) {
+                    float sx = sample_u / fmaxf(m.p_diff, 1.e-6f);
+                    float sy = rng_uniform(rng);
+                    // sample_cosine_hemisphere (shader.wgsl:892-901)
+                    float r = sqrtf(sx);
+                    float s, c;
+                    rt_sincos(RT_TWO_PI * sy, &s, &c);
+                    float x = r * c, y = r * s;
+                    wi = v3(x, y, sqrtf(fmaxf(0.0f, 1.0f - x * x - y * y)));
+                } else {
+                    float sx = (sample_u - m.p_diff) / fmaxf(m.p_spec, 1.e-6f);
+                    float sy = rng_uniform(rng);
+                    V3 h = sample_ggx_vndf(sx, sy, wo, m.alpha);
+                    wi = reflect(-wo, h);
+                    blocked = wi.z <= 0.0f;
+                }
+                if (blocked) {
+                    done = true;  // direction (1,0,0) with pdf 0: path ends, L kept
+                } else {
+                    V3 f;
+                    float pdf;
+                    bsdf_eval_pdf(wo, wi, m, f, pdf);
+                    V3 wi_world = to_world(frame, wi);
+                    if (dot(n, wi_world) < 0.0f) {
+                        L = v3(0.f, 1.f, 0.f);
+                        done = true;
+                    } else if (pdf <= 0.0f) {
+                        done = true;
+                    } else {
+                        float cos_theta = fmaxf(0.0f, dot(n, wi_world));
+                        T = T * (f * (cos_theta / pdf));
+                        if (length(T) < 0.001f) {
+                            done = true;
+                        } else {
+                            last_pdf = pdf;
+                            o = point;
+                            d = wi_world;
+                        }
+                    }
+                }
+            }
+        }
+
+        bounce++;
+        if (done || bounce >= p.max_bounces) {
+            acc = acc + L;  // shader.wgsl:1367-1368
+            sample++;
+            if (sample < sample_end) {
+                camera_ray(p.camera, sin_half_fov, px, py, p.width, p.height, sample, rng, o, d);
+                cn.paths++;
+                T = v3s(1.f);
+                L = v3s(0.f);
+                last_pdf = 1.0f;
+                bounce = 0u;
+            }
+        }
+    }
+
+    if (active) {
+        if (p.max_bounces == 0u) cn.paths += p.sample_count;
+        p.accum[pixel] = make_float4(acc.x, acc.y, acc.z, 1.0f);  // shader.wgsl:1371
+    }
+    flush_counts(cn, p.counters, COUNT);
+}
+
+struct FirstHitParams {
+    SceneView scene;
+    CameraParams camera;
+    uint32_t* slot_out;
+    float* t_out;
+    unsigned long long* counters;
+    uint32_t width, height, sample;
+};
+
+template <bool COUNT, int STACK_CAP>
+__global__ void __launch_bounds__(kBlockThreads) first_hit_kernel(const FirstHitParams p) {
+    uint32_t px, py;
+    thread_pixel(px, py);
+    Counts cn;
+    memset(&cn, 0, sizeof cn);
+    if (px < p.width && py < p.height) {
+        uint32_t stack[STACK_CAP];
+        uint32_t rng;
+        V3 o, d;
+        camera_ray(p.camera, rt_sin(p.camera.fov_y / 2.0f), px, py, p.width, p.height, p.sample,
+                   rng, o, d);
+        Hit hit;
+        cn.paths++;
+        cn.rays++;
+        cast_ray<COUNT>(p.scene, o, d, hit, stack, cn);
+        uint32_t slot = hit.rec;
+        if (hit.rec != 0xFFFFFFFFu && hit.rec >= p.scene.slot_count) {
+            uint32_t k = hit.rec - p.scene.slot_count;
+            slot = k < p.scene.sphere_count ? (0x80000000u | k)
+                                            : (0x90000000u | (k - p.scene.sphere_count));
+        }
+        size_t i = (size_t)py * p.width + px;
+        p.slot_out[i] = slot;
+        p.t_out[i] = hit.rec != 0xFFFFFFFFu ? hit.t : 0.0f;
+    }
+    flush_counts(cn, p.counters, COUNT);
+}
+
+__global__ void bake_materials_kernel(const float* src, float4* dst, uint32_t count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) bake_material(src + 12u * (size_t)i, dst + 3u * (size_t)i);
+}
+
+__global__ void clear_accum_kernel(float4* accum, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) accum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// Present pass: src/shaders/hdr.wgsl:3-22 over out_texture = accum / sample_total (f16).
+__global__ void tonemap_kernel(const float4* accum, uint8_t* rgb8, size_t count, float inv_unused,
+                               float sample_total) {
+    (void)inv_unused;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float4 a = accum[i];
+    // pixel_color = total_light / f32(sample_count + 1), stored to an rgba16float texture.
+    float h[3] = {__half2float(__float2half_rn(a.x / sample_total)),
+                  __half2float(__float2half_rn(a.y / sample_total)),
+                  __half2float(__float2half_rn(a.z / sample_total))};
+    float out[3];
+    if (h[0] < 0.0f || h[1] < 0.0f || h[2] < 0.0f) {
+        out[0] = 1.0f; out[1] = 0.0f; out[2] = 1.0f;
+    } else {
+        // WGSL mat3x3 constructors take columns.
+        float v[3] = {(0.59719f * h[0] + 0.35458f * h[1]) + 0.04823f * h[2],
+                      (0.07600f * h[0] + 0.90834f * h[1]) + 0.01566f * h[2],
+                      (0.02840f * h[0] + 0.13383f * h[1]) + 0.83777f * h[2]};
+        float r[3];
+        for (int k = 0; k < 3; k++) {
+            float av = v[k] * (v[k] + 0.0245786f) - 0.000090537f;
+            float bv = v[k] * (0.983729f * v[k] + 0.4329510f) + 0.238081f;
+            r[k] = av / bv;
+        }
+        out[0] = (1.60475f * r[0] + -0.53108f * r[1]) + -0.07367f * r[2];
+        out[1] = (-0.10208f * r[0] + 1.10813f * r[1]) + -0.00605f * r[2];
+        out[2] = (-0.00327f * r[0] + -0.07276f * r[1]) + 1.07602f * r[2];
+        for (int k = 0; k < 3; k++) out[k] = fminf(fmaxf(out[k], 0.0f), 1.0f);
+    }
+    for (int k = 0; k < 3; k++) {
+        // linear -> sRGB, as the sRGB surface format does on store.
+        float c = out[k];
+        float s = c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+        rgb8[i * 3 + k] = (uint8_t)(fminf(fmaxf(s, 0.0f), 1.0f) * 255.0f + 0.5f);
+    }
+}
+
+// =====================================================================================
+// Host side
+// =====================================================================================
+
+namespace {
+
+std::mutex g_error_mutex;
+std::string g_global_error;
+
+}  // namespace
+
+struct RtContext {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    std::string error;
+
+    // scene
+    float4* d_nodes = nullptr;
+    float4* d_records = nullptr;
+    float4* d_tri_normals = nullptr;
+    float4* d_materials = nullptr;
+    SceneView scene{};
+    uint32_t bvh_depth = 0;
+    bool has_scene = false;
+
+    // environments
+    struct Env {
+        cudaArray_t array = nullptr;
+        cudaTextureObject_t texture = 0;
+        float4* d_alias = nullptr;
+        uint32_t width = 0, height = 0;
+    };
+    std::vector<Env> envs;
+
+    CameraParams camera{};
+    bool has_camera = false;
+
+    uint32_t width = 0, height = 0;
+    float4* d_accum_own = nullptr;
+    float4* d_accum = nullptr;
+
+    unsigned long long* d_counters = nullptr;
+    bool detailed = false;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+int fail(RtContext* ctx, int status, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) {
+        ctx->error = buf;
+    } else {
+        std::lock_guard<std::mutex> lock(g_error_mutex);
+        g_global_error = buf;
+    }
+    return status;
+}
+
+#define RT_CUDA(ctx, expr)                                                                   \
+    do {                                                                                     \
+        cudaError_t e_ = (expr);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? RT_ERR_OUT_OF_MEMORY          \
+                                                             : RT_ERR_CUDA,                  \
+                        "%s failed: %s", #expr, cudaGetErrorString(e_));                     \
+    } while (0)
+
+void free_scene(RtContext* ctx) {
+    cudaFree(ctx->d_nodes);
+    cudaFree(ctx->d_records);
+    cudaFree(ctx->d_tri_normals);
+    cudaFree(ctx->d_materials);
+    ctx->d_nodes = ctx->d_records = ctx->d_tri_normals = ctx->d_materials = nullptr;
+    ctx->has_scene = false;
+}
+
+void free_envs(RtContext* ctx) {
+    for (auto& e : ctx->envs) {
+        if (e.texture) cudaDestroyTextureObject(e.texture);
+        if (e.array) cudaFreeArray(e.array);
+        cudaFree(e.d_alias);
+    }
+    ctx->envs.clear();
+}
+
+inline float bits(uint32_t u) {
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// tree_depth (src/bvh.rs:124-134) of the flattened array, iteratively; also validates
+// child / primitive ranges so a malformed upload cannot send a kernel out of bounds.
+bool validate_bvh(const RtSceneDesc& s, uint32_t* depth_out, std::string* why) {
+    struct Item {
+        uint32_t node, depth;
+    };
+    std::vector<Item> todo;
+    todo.push_back({0u, 0u});
+    uint32_t max_depth = 0;
+    uint64_t visited = 0;
+    while (!todo.empty()) {
+        Item it = todo.back();
+        todo.pop_back();
+        if (it.node >= s.bvh_node_count) {
+            *why = "BVH child index out of range";
+            return false;
+        }
+        if (++visited > (uint64_t)s.bvh_node_count) {
+            *why = "BVH is not a tree";
+            return false;
+        }
+        const RtBvhNode& n = s.bvh_nodes[it.node];
+        if (it.depth > max_depth) max_depth = it.depth;
+        if (n.primitives_len > 0) {
+            if ((uint64_t)n.primitives_or_second_child_index + n.primitives_len > s.primitive_count) {
+                *why = "BVH leaf primitive range out of range";
+                return false;
+            }
+            if (n.primitives_len > 0x3FFFFFFFu) {
+                *why = "BVH leaf too large";
+                return false;
+            }
+        } else {
+            if (n.split_axis > 2u) {
+                *why = "BVH split axis out of range";
+                return false;
+            }
+            todo.push_back({it.node + 1u, it.depth + 1u});
+            todo.push_back({n.primitives_or_second_child_index, it.depth + 1u});
+        }
+    }
+    *depth_out = max_depth;
+    return true;
+}
+
+template <bool COUNT>
+cudaError_t launch_render(const RenderParams& p, uint32_t depth, cudaStream_t stream) {
+    dim3 grid((p.width + kTileW - 1) / kTileW, (p.height + kTileH - 1) / kTileH);
+    dim3 block(kBlockThreads);
+    if (depth <= 8) render_kernel<COUNT, 8><<<grid, block, 0, stream>>>(p);
+    else if (depth <= 16) render_kernel<COUNT, 16><<<grid, block, 0, stream>>>(p);
+    else if (depth <= 32) render_kernel<COUNT, 32><<<grid, block, 0, stream>>>(p);
+    else render_kernel<COUNT, 64><<<grid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <bool COUNT>
+cudaError_t launch_first_hit(const FirstHitParams& p, uint32_t depth, cudaStream_t stream) {
+    dim3 grid((p.width + kTileW - 1) / kTileW, (p.height + kTileH - 1) / kTileH);
+    dim3 block(kBlockThreads);
+    if (depth <= 8) first_hit_kernel<COUNT, 8><<<grid, block, 0, stream>>>(p);
+    else if (depth <= 16) first_hit_kernel<COUNT, 16><<<grid, block, 0, stream>>>(p);
+    else if (depth <= 32) first_hit_kernel<COUNT, 32><<<grid, block, 0, stream>>>(p);
+    else first_hit_kernel<COUNT, 64><<<grid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+int check_ready(RtContext* ctx, uint32_t env_index, bool need_env) {
+    if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "no scene uploaded (rt_upload_scene)");
+    if (!ctx->has_camera) return fail(ctx, RT_ERR_STATE, "no camera set (rt_set_camera)");
+    if (!ctx->width || !ctx->height || (!ctx->d_accum && need_env))
+        return fail(ctx, RT_ERR_STATE, "no render target (rt_resize)");
+    if (need_env && env_index >= ctx->envs.size())
+        return fail(ctx, RT_ERR_INVALID_ARGUMENT, "environment index %u out of range (%zu loaded)",
+                    env_index, ctx->envs.size());
+    return RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rt_backend_version(void) { return "rt_backend 0.1 (sm_100a)"; }
+
+int rt_device_count(int* count) {
+    if (!count) return RT_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(nullptr, RT_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    }
+    return RT_OK;
+}
+
+int rt_create(int device, RtContext** out) {
+    if (!out) return RT_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, RT_ERR_CUDA, "no usable CUDA device (%s); this backend has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+    if (device < 0 || device >= count)
+        return fail(nullptr, RT_ERR_INVALID_ARGUMENT, "device ordinal %d out of range (0..%d)",
+                    device, count - 1);
+    RtContext* ctx = new RtContext();
+    ctx->device = device;
+    auto bail = [&](const char* what, cudaError_t err) {
+        int st = fail(nullptr, RT_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(err));
+        delete ctx;
+        return st;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail("cudaStreamCreate", e);
+    ctx->stream = ctx->own_stream;
+    if ((e = cudaEventCreate(&ctx->ev_start)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev_stop)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMalloc(&ctx->d_counters, sizeof(RtCounters))) != cudaSuccess)
+        return bail("cudaMalloc(counters)", e);
+    if ((e = cudaMemset(ctx->d_counters, 0, sizeof(RtCounters))) != cudaSuccess)
+        return bail("cudaMemset(counters)", e);
+    *out = ctx;
+    return RT_OK;
+}
+
+void rt_destroy(RtContext* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    free_envs(ctx);
+    cudaFree(ctx->d_accum_own);
+    cudaFree(ctx->d_counters);
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* rt_last_error(const RtContext* ctx) {
+    if (ctx) return ctx->error.c_str();
+    std::lock_guard<std::mutex> lock(g_error_mutex);
+    static thread_local std::string copy;
+    copy = g_global_error;
+    return copy.c_str();
+}
+
+int rt_upload_scene(RtContext* ctx, const RtSceneDesc* s) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!s || !s->bvh_nodes || !s->bvh_node_count || !s->primitives || !s->primitive_count ||
+        !s->materials || !s->material_count)
+        return fail(ctx, RT_ERR_INVALID_ARGUMENT, "scene needs materials, primitives and BVH nodes");
+    if ((s->sphere_count && !s->spheres) || (s->plane_count && !s->planes) ||
+        (s->triangle_count && (!s->triangles || !s->vertices || !s->normals)))
+        return fail(ctx, RT_ERR_INVALID_ARGUMENT, "scene array pointer is NULL with a non-zero count");
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    uint32_t depth = 0;
+    std::string why;
+    if (!validate_bvh(*s, &depth, &why)) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "%s", why.c_str());
+    if (depth > 64)
+        return fail(ctx, RT_ERR_INVALID_ARGUMENT,
+                    "BVH depth %u exceeds the reference's 64-entry traversal stack", depth);
+
+    // ---- re-layout ----
+    std::vector<float4> nodes((size_t)s->bvh_node_count * 2);
+    for (uint32_t i = 0; i < s->bvh_node_count; i++) {
+        const RtBvhNode& n = s->bvh_nodes[i];
+        uint32_t meta = n.primitives_len > 0 ? n.primitives_len : (n.split_axis << 30);
+        nodes[2 * (size_t)i] = make_float4(n.min[0], n.min[1], n.min[2], bits(n.primitives_or_second_child_index));
+        nodes[2 * (size_t)i + 1] = make_float4(n.max[0], n.max[1], n.max[2], bits(meta));
+    }
+
+    const uint32_t slots = s->primitive_count;
+    const size_t rec_count = (size_t)slots + s->sphere_count + s->plane_count;
+    std::vector<float4> records(rec_count * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<float4> tri_normals((size_t)slots * 3, make_float4(0.f, 0.f, 0.f, 0.f));
+
+    auto write_sphere = [&](size_t rec, const RtSphere& sp) {
+        records[rec * 4 + 0] = make_float4(sp.pos[0], sp.pos[1], sp.pos[2], bits(0u));
+        records[rec * 4 + 1] = make_float4(sp.radius, sp.radius * sp.radius, bits(sp.material_id), 0.f);
+    };
+    auto write_plane = [&](size_t rec, const RtPlane& pl) {
+        records[rec * 4 + 0] = make_float4(pl.pos[0], pl.pos[1], pl.pos[2], bits(1u));
+        records[rec * 4 + 1] = make_float4(pl.normal[0], pl.normal[1], pl.normal[2], bits(pl.material_id));
+        records[rec * 4 + 2] = make_float4(pl.base_change[0][0], pl.base_change[1][0], pl.base_change[2][0], 0.f);
+        records[rec * 4 + 3] = make_float4(pl.base_change[0][2], pl.base_change[1][2], pl.base_change[2][2], 0.f);
+    };
+    for (uint32_t slot = 0; slot < slots; slot++) {
+        const RtPrimitiveInfo& info = s->primitives[slot];
+        if (info.primitive_type == 0) {
+            if (info.index >= s->sphere_count)
+                return fail(ctx, RT_ERR_INVALID_ARGUMENT, "primitive %u: sphere index out of range", slot);
+            if (s->spheres[info.index].material_id >= s->material_count)
+                return fail(ctx, RT_ERR_INVALID_ARGUMENT, "sphere %u: material out of range", info.index);
+            write_sphere(slot, s->spheres[info.index]);
+        } else if (info.primitive_type == 1) {
+            if (info.index >= s->plane_count)
+                return fail(ctx, RT_ERR_INVALID_ARGUMENT, "primitive %u: plane index out of range", slot);
+            if (s->planes[info.index].material_id >= s->material_count)
+                return fail(ctx, RT_ERR_INVALID_ARGUMENT, "plane %u: material out of range", info.index);
+            write_plane(slot, s->planes[info.index]);
+        } else if (info.primitive_type == 2) {
+            if (info.index >= s->triangle_count)
+                return fail(ctx, RT_ERR_INVALID_ARGUMENT, "primitive %u: triangle index out of range", slot);
+            const RtTriangle& t = s->triangles[info.index];
+            if (t.vertex_0 >= s->vertex_count || t.vertex_1 >= s->vertex_count ||
+                t.vertex_2 >= s->vertex_count || t.normal_0 >= s->normal_count ||
+                t.normal_1 >= s->normal_count || t.normal_2 >= s->normal_count ||
+                t.material_id >= s->material_count)
+                return fail(ctx, RT_ERR_INVALID_ARGUMENT, "triangle %u: index out of range", info.index);
+            const RtVec3 &a = s->vertices[t.vertex_0], &b = s->vertices[t.vertex_1],
+                         &c = s->vertices[t.vertex_2];
+            // edge_0 = b - a, edge_1 = c - a (shader.wgsl:415-416): single f32 subtractions,
+            // so hoisting them to upload time leaves every bit unchanged.
+            records[(size_t)slot * 4 + 0] = make_float4(a.x, a.y, a.z, bits(2u));
+            records[(size_t)slot * 4 + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, bits(t.material_id));
+            records[(size_t)slot * 4 + 2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.f);
+            const RtVec3 &n0 = s->normals[t.normal_0], &n1 = s->normals[t.normal_1],
+                         &n2 = s->normals[t.normal_2];
+            tri_normals[(size_t)slot * 3 + 0] = make_float4(n0.x, n0.y, n0.z, 0.f);
+            tri_normals[(size_t)slot * 3 + 1] = make_float4(n1.x, n1.y, n1.z, 0.f);
+            tri_normals[(size_t)slot * 3 + 2] = make_float4(n2.x, n2.y, n2.z, 0.f);
+        } else {
+            return fail(ctx, RT_ERR_INVALID_ARGUMENT, "primitive %u: unknown type %u", slot,
+                        info.primitive_type);
+        }
+    }
+    for (uint32_t i = 0; i < s->sphere_count; i++) write_sphere((size_t)slots + i, s->spheres[i]);
+    for (uint32_t i = 0; i < s->plane_count; i++)
+        write_plane((size_t)slots + s->sphere_count + i, s->planes[i]);
+
+    // ---- upload ----
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    free_scene(ctx);
+    float* d_raw_materials = nullptr;
+    RT_CUDA(ctx, cudaMalloc(&ctx->d_nodes, nodes.size() * sizeof(float4)));
+    RT_CUDA(ctx, cudaMalloc(&ctx->d_records, records.size() * sizeof(float4)));
+    RT_CUDA(ctx, cudaMalloc(&ctx->d_tri_normals, tri_normals.size() * sizeof(float4)));
+    RT_CUDA(ctx, cudaMalloc(&ctx->d_materials, (size_t)s->material_count * 3 * sizeof(float4)));
+    RT_CUDA(ctx, cudaMalloc(&d_raw_materials, (size_t)s->material_count * sizeof(RtMaterial)));
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_nodes, nodes.data(), nodes.size() * sizeof(float4),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_records, records.data(), records.size() * sizeof(float4),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tri_normals, tri_normals.data(),
+                                 tri_normals.size() * sizeof(float4), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(d_raw_materials, s->materials,
+                                 (size_t)s->material_count * sizeof(RtMaterial),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    bake_materials_kernel<<<(s->material_count + 127) / 128, 128, 0, ctx->stream>>>(
+        d_raw_materials, ctx->d_materials, s->material_count);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_raw_materials);
+
+    ctx->scene.nodes = ctx->d_nodes;
+    ctx->scene.records = ctx->d_records;
+    ctx->scene.tri_normals = ctx->d_tri_normals;
+    ctx->scene.materials = ctx->d_materials;
+    ctx->scene.slot_count = slots;
+    ctx->scene.sphere_count = s->sphere_count;
+    ctx->scene.plane_count = s->plane_count;
+    ctx->bvh_depth = depth;
+    ctx->has_scene = true;
+    return RT_OK;
+}
+
+int rt_upload_environments(RtContext* ctx, const RtEnvironmentDesc* envs, uint32_t count) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!envs || !count) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "no environments given");
+    for (uint32_t i = 0; i < count; i++)
+        if (!envs[i].width || !envs[i].height || !envs[i].rgba || !envs[i].alias ||
+            (uint64_t)envs[i].width * envs[i].height > 0xFFFFFFFFull)
+            return fail(ctx, RT_ERR_INVALID_ARGUMENT, "environment %u is incomplete", i);
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    free_envs(ctx);
+    for (uint32_t i = 0; i < count; i++) {
+        RtContext::Env e;
+        e.width = envs[i].width;
+        e.height = envs[i].height;
+        size_t texels = (size_t)e.width * e.height;
+        cudaChannelFormatDesc desc = cudaCreateChannelDesc<float4>();
+        RT_CUDA(ctx, cudaMallocArray(&e.array, &desc, e.width, e.height));
+        RT_CUDA(ctx, cudaMemcpy2DToArray(e.array, 0, 0, envs[i].rgba, (size_t)e.width * 16,
+                                         (size_t)e.width * 16, e.height, cudaMemcpyHostToDevice));
+        cudaResourceDesc res;
+        memset(&res, 0, sizeof res);
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = e.array;
+        cudaTextureDesc tex;
+        memset(&tex, 0, sizeof tex);
+        tex.addressMode[0] = tex.addressMode[1] = cudaAddressModeClamp;  // state.rs:135-137
+        tex.filterMode = cudaFilterModePoint;  // bilinear blend is done in f32 in the kernel
+        tex.readMode = cudaReadModeElementType;
+        tex.normalizedCoords = 0;
+        RT_CUDA(ctx, cudaCreateTextureObject(&e.texture, &res, &tex, nullptr));
+        RT_CUDA(ctx, cudaMalloc(&e.d_alias, texels * sizeof(float4)));
+        RT_CUDA(ctx, cudaMemcpy(e.d_alias, envs[i].alias, texels * sizeof(RtAliasEntry),
+                                cudaMemcpyHostToDevice));
+        ctx->envs.push_back(e);
+    }
+    return RT_OK;
+}
+
+int rt_set_camera(RtContext* ctx, const RtCameraUniform* cam) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!cam) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "camera is NULL");
+    for (int i = 0; i < 3; i++) ctx->camera.pos[i] = cam->pos[i];
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) ctx->camera.rot[c * 3 + r] = cam->rot[c][r];
+    ctx->camera.fov_y = cam->fov_y;
+    ctx->has_camera = true;
+    return RT_OK;
+}
+
+int rt_clear(RtContext* ctx) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!ctx->d_accum) return fail(ctx, RT_ERR_STATE, "no render target (rt_resize)");
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t count = (size_t)ctx->width * ctx->height;
+    clear_accum_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_accum, count);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_resize(RtContext* ctx, uint32_t width, uint32_t height) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!width || !height || (uint64_t)width * height > 0x7FFFFFFFull)
+        return fail(ctx, RT_ERR_INVALID_ARGUMENT, "invalid resolution %ux%u", width, height);
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bool external = ctx->d_accum && ctx->d_accum != ctx->d_accum_own;
+    if (external && (width != ctx->width || height != ctx->height))
+        return fail(ctx, RT_ERR_STATE, "cannot resize while an external accumulation buffer is bound");
+    if (!external) {
+        cudaFree(ctx->d_accum_own);
+        ctx->d_accum_own = nullptr;
+        ctx->d_accum = nullptr;
+        RT_CUDA(ctx, cudaMalloc(&ctx->d_accum_own, (size_t)width * height * sizeof(float4)));
+        ctx->d_accum = ctx->d_accum_own;
+    }
+    ctx->width = width;
+    ctx->height = height;
+    return rt_clear(ctx);
+}
+
+int rt_bind_accum(RtContext* ctx, void* device_rgba) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!ctx->width || !ctx->height) return fail(ctx, RT_ERR_STATE, "call rt_resize first");
+    if (device_rgba && ((uintptr_t)device_rgba & 15u))
+        return fail(ctx, RT_ERR_INVALID_ARGUMENT, "accumulation buffer must be 16-byte aligned");
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->d_accum = device_rgba ? (float4*)device_rgba : ctx->d_accum_own;
+    return RT_OK;
+}
+
+int rt_accum_device_ptr(RtContext* ctx, void** out) {
+    if (!ctx || !out) return RT_ERR_INVALID_ARGUMENT;
+    *out = ctx->d_accum;
+    return RT_OK;
+}
+
+int rt_render(RtContext* ctx, uint32_t sample_begin, uint32_t sample_count, uint32_t max_bounces,
+              uint32_t env_index) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    int st = check_ready(ctx, env_index, true);
+    if (st != RT_OK) return st;
+    if (sample_count == 0) return RT_OK;
+    if ((uint64_t)sample_begin + sample_count > 0xFFFFFFFFull)
+        return fail(ctx, RT_ERR_INVALID_ARGUMENT, "sample range overflows u32");
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RenderParams p;
+    p.scene = ctx->scene;
+    const RtContext::Env& e = ctx->envs[env_index];
+    p.env.texture = e.texture;
+    p.env.alias = e.d_alias;
+    p.env.width = e.width;
+    p.env.height = e.height;
+    p.camera = ctx->camera;
+    p.accum = ctx->d_accum;
+    p.counters = ctx->d_counters;
+    p.width = ctx->width;
+    p.height = ctx->height;
+    p.sample_begin = sample_begin;
+    p.sample_count = sample_count;
+    p.max_bounces = max_bounces;
+    cudaError_t e2 = ctx->detailed ? launch_render<true>(p, ctx->bvh_depth, ctx->stream)
+                                   : launch_render<false>(p, ctx->bvh_depth, ctx->stream);
+    ctx->launches++;
+    if (e2 != cudaSuccess)
+        return fail(ctx, RT_ERR_CUDA, "render kernel launch failed: %s", cudaGetErrorString(e2));
+    return RT_OK;
+}
+
+int rt_first_hit(RtContext* ctx, uint32_t sample_index, uint32_t* slot_out, float* t_out) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!slot_out) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "slot_out is NULL");
+    int st = check_ready(ctx, 0, false);
+    if (st != RT_OK) return st;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t count = (size_t)ctx->width * ctx->height;
+    uint32_t* d_slot = nullptr;
+    float* d_t = nullptr;
+    RT_CUDA(ctx, cudaMalloc(&d_slot, count * 4));
+    cudaError_t e = cudaMalloc(&d_t, count * 4);
+    if (e != cudaSuccess) {
+        cudaFree(d_slot);
+        return fail(ctx, RT_ERR_OUT_OF_MEMORY, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+    FirstHitParams p;
+    p.scene = ctx->scene;
+    p.camera = ctx->camera;
+    p.slot_out = d_slot;
+    p.t_out = d_t;
+    p.counters = ctx->d_counters;
+    p.width = ctx->width;
+    p.height = ctx->height;
+    p.sample = sample_index;
+    e = ctx->detailed ? launch_first_hit<true>(p, ctx->bvh_depth, ctx->stream)
+                      : launch_first_hit<false>(p, ctx->bvh_depth, ctx->stream);
+    ctx->launches++;
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(slot_out, d_slot, count * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && t_out)
+        e = cudaMemcpyAsync(t_out, d_t, count * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_slot);
+    cudaFree(d_t);
+    if (e != cudaSuccess)
+        return fail(ctx, RT_ERR_CUDA, "first-hit pass failed: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
+int rt_sync(RtContext* ctx) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_read_accum(RtContext* ctx, float* rgba_out) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!rgba_out) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "output pointer is NULL");
+    if (!ctx->d_accum) return fail(ctx, RT_ERR_STATE, "no render target (rt_resize)");
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaMemcpyAsync(rgba_out, ctx->d_accum,
+                                 (size_t)ctx->width * ctx->height * sizeof(float4),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_write_accum(RtContext* ctx, const float* rgba_in) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!rgba_in) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "input pointer is NULL");
+    if (!ctx->d_accum) return fail(ctx, RT_ERR_STATE, "no render target (rt_resize)");
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_accum, rgba_in,
+                                 (size_t)ctx->width * ctx->height * sizeof(float4),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_tonemap_rgb8(RtContext* ctx, uint32_t sample_total, uint8_t* rgb8_out) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!rgb8_out || !sample_total)
+        return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rgb8_out NULL or sample_total 0");
+    if (!ctx->d_accum) return fail(ctx, RT_ERR_STATE, "no render target (rt_resize)");
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t count = (size_t)ctx->width * ctx->height;
+    uint8_t* d_rgb = nullptr;
+    RT_CUDA(ctx, cudaMalloc(&d_rgb, count * 3));
+    tonemap_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->d_accum, d_rgb, count, 0.f, (float)sample_total);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(rgb8_out, d_rgb, count * 3, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_rgb);
+    if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "tone-map pass failed: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
+int rt_set_detailed_counters(RtContext* ctx, int enabled) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    ctx->detailed = enabled != 0;
+    return RT_OK;
+}
+
+int rt_reset_counters(RtContext* ctx) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(RtCounters), ctx->stream));
+    return RT_OK;
+}
+
+int rt_get_counters(RtContext* ctx, RtCounters* out) {
+    if (!ctx || !out) return RT_ERR_INVALID_ARGUMENT;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_counters, sizeof(RtCounters), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_set_stream(RtContext* ctx, void* cuda_stream) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return RT_OK;
+}
+
+int rt_timer_start(RtContext* ctx) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    return RT_OK;
+}
+
+int rt_timer_stop(RtContext* ctx, float* elapsed_ms) {
+    if (!ctx || !elapsed_ms) return RT_ERR_INVALID_ARGUMENT;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+    RT_CUDA(ctx, cudaEventSynchronize(ctx->ev_stop));
+    RT_CUDA(ctx, cudaEventElapsedTime(elapsed_ms, ctx->ev_start, ctx->ev_stop));
+    return RT_OK;
+}
+
+uint64_t rt_launch_count(const RtContext* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
+
+// =====================================================================================
+// Single-process multi-GPU group: sample split + NCCL sum-reduce. NCCL is bound lazily
+// with dlopen so that single-GPU users do not need the library on their loader path.
+// =====================================================================================
+
+namespace {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t,
+                           cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.handle) return;
+        api.CommInitAll = (decltype(api.CommInitAll))dlsym(api.handle, "ncclCommInitAll");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+        api.Reduce = (decltype(api.Reduce))dlsym(api.handle, "ncclReduce");
+        api.GroupStart = (decltype(api.GroupStart))dlsym(api.handle, "ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.handle, "ncclGroupEnd");
+        api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+        api.ok = api.CommInitAll && api.CommDestroy && api.Reduce && api.GroupStart &&
+                 api.GroupEnd && api.GetErrorString;
+    });
+    return api;
+}
+
+}  // namespace
+
+struct RtGroup {
+    std::vector<RtContext*> ctxs;
+    std::vector<ncclComm_t> comms;
+};
+
+extern "C" {
+
+int rt_group_create(int count, const int* devices, RtGroup** out) {
+    if (!out || count <= 0 || !devices) return RT_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    RtGroup* g = new RtGroup();
+    for (int i = 0; i < count; i++) {
+        RtContext* c = nullptr;
+        int st = rt_create(devices[i], &c);
+        if (st != RT_OK) {
+            rt_group_destroy(g);
+            return st;
+        }
+        g->ctxs.push_back(c);
+    }
+    if (count > 1) {
+        NcclApi& api = nccl_api();
+        if (!api.ok) {
+            rt_group_destroy(g);
+            return fail(nullptr, RT_ERR_NCCL, "libnccl.so.2 could not be loaded: %s",
+                        dlerror() ? dlerror() : "missing symbols");
+        }
+        g->comms.resize((size_t)count);
+        ncclResult_t r = api.CommInitAll(g->comms.data(), count, devices);
+        if (r != ncclSuccess) {
+            g->comms.clear();
+            rt_group_destroy(g);
+            return fail(nullptr, RT_ERR_NCCL, "ncclCommInitAll failed: %s", api.GetErrorString(r));
+        }
+    }
+    *out = g;
+    return RT_OK;
+}
+
+void rt_group_destroy(RtGroup* g) {
+    if (!g) return;
+    for (ncclComm_t c : g->comms) nccl_api().CommDestroy(c);
+    for (RtContext* c : g->ctxs) rt_destroy(c);
+    delete g;
+}
+
+int rt_group_size(const RtGroup* g) { return g ? (int)g->ctxs.size() : 0; }
+
+RtContext* rt_group_context(RtGroup* g, int rank) {
+    if (!g || rank < 0 || rank >= (int)g->ctxs.size()) return nullptr;
+    return g->ctxs[(size_t)rank];
+}
+
+int rt_group_render(RtGroup* g, uint32_t sample_begin, uint32_t sample_count, uint32_t max_bounces,
+                    uint32_t env_index) {
+    if (!g) return RT_ERR_INVALID_ARGUMENT;
+    uint32_t n = (uint32_t)g->ctxs.size();
+    for (uint32_t r = 0; r < n; r++) {
+        // Contiguous, disjoint sample ranges whose union is the single-GPU range.
+        uint32_t lo = (uint32_t)((uint64_t)sample_count * r / n);
+        uint32_t hi = (uint32_t)((uint64_t)sample_count * (r + 1) / n);
+        int st = rt_render(g->ctxs[r], sample_begin + lo, hi - lo, max_bounces, env_index);
+        if (st != RT_OK) return st;
+    }
+    return RT_OK;
+}
+
+int rt_group_reduce(RtGroup* g, int root) {
+    if (!g || root < 0 || root >= (int)g->ctxs.size()) return RT_ERR_INVALID_ARGUMENT;
+    if (g->ctxs.size() == 1) return RT_OK;
+    NcclApi& api = nccl_api();
+    RtContext* r0 = g->ctxs[(size_t)root];
+    size_t floats = (size_t)r0->width * r0->height * 4;
+    for (RtContext* c : g->ctxs)
+        if (c->width != r0->width || c->height != r0->height || !c->d_accum)
+            return fail(r0, RT_ERR_STATE, "group members have different render targets");
+    ncclResult_t r = api.GroupStart();
+    for (size_t i = 0; r == ncclSuccess && i < g->ctxs.size(); i++) {
+        RtContext* c = g->ctxs[i];
+        cudaSetDevice(c->device);
+        r = api.Reduce(c->d_accum, c->d_accum, floats, ncclFloat32, ncclSum, root, g->comms[i],
+                       c->stream);
+    }
+    ncclResult_t r2 = api.GroupEnd();
+    if (r == ncclSuccess) r = r2;
+    if (r != ncclSuccess)
+        return fail(r0, RT_ERR_NCCL, "ncclReduce failed: %s", api.GetErrorString(r));
+    return RT_OK;
+}
+
+int rt_group_sync(RtGroup* g) {
+    if (!g) return RT_ERR_INVALID_ARGUMENT;
+    for (RtContext* c : g->ctxs) {
+        int st = rt_sync(c);
+        if (st != RT_OK) return st;
+    }
+    return RT_OK;
+}
+
+}  // extern "C"
