@@ -206,7 +206,7 @@ def main():
     state.set_stream(stream.cuda_stream)
     host_accum = torch.empty((height, width, 4), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    sample_begin = rank * spp
+    sample_begin, _ = rt.samplesplit.weak_range(spp, rank)
 
     def barrier():
         if world > 1:
@@ -217,7 +217,7 @@ def main():
         accum.zero_()
         state.render_range(sample_begin, spp)
         if world > 1:
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+            rt.samplesplit.reduce_accumulation(accum, dst=0)
 
     def e2e_step():
         # Host buffers -> device (scene arrays, camera), render, reduce, device -> host.
@@ -226,7 +226,7 @@ def main():
         accum.zero_()
         state.render_range(sample_begin, spp)
         if world > 1:
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+            rt.samplesplit.reduce_accumulation(accum, dst=0)
         host_accum.copy_(accum, non_blocking=True)
         stream.synchronize()
 
@@ -257,7 +257,7 @@ def main():
         state.render_range(sample_begin, spp)
         e1.record()
         if world > 1:
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+            rt.samplesplit.reduce_accumulation(accum, dst=0)
         e2.record()
         barrier()
         step_ms.append(es.elapsed_time(e2))

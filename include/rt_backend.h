@@ -27,7 +27,7 @@ typedef struct RtGroup RtGroup;
 
 /* Work counters. rays / shadow_rays / paths are always maintained; the rest only when
  * detailed counting is enabled (rt_set_detailed_counters), at a throughput cost. The
- * layout matches the oracle's counters so tests compare them field by field. */
+ * layout is fixed so tests can compare the fields one by one. */
 typedef struct RtCounters {
     uint64_t paths;           /* pixel-samples traced (shader.wgsl main invocations)        */
     uint64_t rays;            /* closest-hit cast_ray calls (shader.wgsl:1221)              */
@@ -105,8 +105,11 @@ int rt_set_detailed_counters(RtContext* ctx, int enabled);
 int rt_reset_counters(RtContext* ctx);
 int rt_get_counters(RtContext* ctx, RtCounters* out); /* synchronises */
 
-/* Stream interop: run on a caller-provided cudaStream_t (NULL = the context's own). */
+/* Stream interop: enqueue on a caller-provided cudaStream_t. The handle is used as is, so
+ * NULL means the CUDA legacy default stream. rt_reset_stream() returns to the context's
+ * own non-blocking stream. */
 int rt_set_stream(RtContext* ctx, void* cuda_stream);
+int rt_reset_stream(RtContext* ctx);
 /* CUDA-event timing on the context's stream. */
 int rt_timer_start(RtContext* ctx);
 int rt_timer_stop(RtContext* ctx, float* elapsed_ms); /* synchronises */

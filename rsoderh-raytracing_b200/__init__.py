@@ -6,7 +6,7 @@ the repo root.
 """
 from .api import (REFERENCE_MAX_BOUNCES, Camera, Environment, EnvironmentMaps, RtError, Scene,
                   SceneBuilder, State, write_pfm, write_png)
-from . import _ffi
+from . import _ffi, samplesplit
 
 __all__ = ["REFERENCE_MAX_BOUNCES", "Camera", "Environment", "EnvironmentMaps", "RtError",
-           "Scene", "SceneBuilder", "State", "write_pfm", "write_png", "_ffi"]
+           "Scene", "SceneBuilder", "State", "write_pfm", "write_png", "_ffi", "samplesplit"]

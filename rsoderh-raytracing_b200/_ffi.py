@@ -10,7 +10,8 @@ import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 HOST_LIB_PATH = os.path.join(_PKG_DIR, "librt_host.so")
-BACKEND_LIB_PATH = os.path.join(_PKG_DIR, "librt_backend.so")
+# RT_BACKEND_LIB selects an alternative build of the SAME backend (kernel tuning variants).
+BACKEND_LIB_PATH = os.environ.get("RT_BACKEND_LIB") or os.path.join(_PKG_DIR, "librt_backend.so")
 
 # Status codes (rt_types.h).
 RT_OK = 0
@@ -157,6 +158,7 @@ BACKEND_SIGNATURES = {
     "rt_reset_counters": (C.c_int, [_vp]),
     "rt_get_counters": (C.c_int, [_vp, C.POINTER(RtCounters)]),
     "rt_set_stream": (C.c_int, [_vp, _vp]),
+    "rt_reset_stream": (C.c_int, [_vp]),
     "rt_timer_start": (C.c_int, [_vp]),
     "rt_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "rt_launch_count": (C.c_uint64, [_vp]),
@@ -176,7 +178,9 @@ def _bind(path: str, signatures: dict) -> C.CDLL:
             f"{os.path.basename(path)} is not built ({path}); run `make` or "
             "`python -c 'import __graft_entry__ as g; g.build()'` at the repo root. "
             "There is no fallback path.")
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    # RTLD_LOCAL: the backend links cudart statically; its symbols must not leak into
+    # other CUDA users in the process (e.g. torch).
+    lib = C.CDLL(path, mode=C.RTLD_LOCAL)
     for name, (restype, argtypes) in signatures.items():
         fn = getattr(lib, name)
         fn.restype = restype

@@ -433,7 +433,11 @@ class State:
         return c.as_dict()
 
     def set_stream(self, cuda_stream: int):
+        """Enqueue on this cudaStream_t handle (0 = the legacy default stream)."""
         self._check(self._lib.rt_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+
+    def reset_stream(self):
+        self._check(self._lib.rt_reset_stream(self._ctx))
 
     def bind_accum(self, device_ptr: int):
         self._check(self._lib.rt_bind_accum(self._ctx, C.c_void_p(device_ptr)))

@@ -57,8 +57,11 @@ RT_DEV void flush_counts(const Counts& cn, unsigned long long* out, bool detaile
     }
 }
 
+#ifndef RT_MIN_BLOCKS
+#define RT_MIN_BLOCKS 6
+#endif
 template <bool COUNT, int STACK_CAP>
-__global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(kBlockThreads, RT_MIN_BLOCKS) render_kernel(const RenderParams p) {
     uint32_t px, py;
     thread_pixel(px, py);
     const bool active = px < p.width && py < p.height;
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParam
         bool done = false;
         Hit hit;
         cn.rays++;
-        cast_ray<COUNT>(p.scene, o, d, hit, stack, cn);
+        trace<COUNT>(p.scene, o, d, false, true, hit, stack, cn);
 
         if (hit.rec == 0xFFFFFFFFu) {
             // shader.wgsl:1222-1231 — escaped into the environment.
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParam
                 if (cos_theta > 0.0f && pdf_env > 0.0f) {
                     Hit shadow;
                     cn.shadow_rays++;
-                    traverse<true, COUNT>(p.scene, point, wi_world, shadow, stack, cn);
+                    trace<COUNT>(p.scene, point, wi_world, true, false, shadow, stack, cn);
                     if (shadow.rec == 0xFFFFFFFFu) {
                         V3 radiance = env_bilinear(p.env, eu, ev);
                         V3 wi = to_local(frame, wi_world);
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(kBlockThreads) first_hit_kernel(const FirstHit
         Hit hit;
         cn.paths++;
         cn.rays++;
-        cast_ray<COUNT>(p.scene, o, d, hit, stack, cn);
+        trace<COUNT>(p.scene, o, d, false, true, hit, stack, cn);
         uint32_t slot = hit.rec;
         if (hit.rec != 0xFFFFFFFFu && hit.rec >= p.scene.slot_count) {
             uint32_t k = hit.rec - p.scene.slot_count;
@@ -937,7 +940,15 @@ int rt_set_stream(RtContext* ctx, void* cuda_stream) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return RT_OK;
+}
+
+int rt_reset_stream(RtContext* ctx) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = ctx->own_stream;
     return RT_OK;
 }
 

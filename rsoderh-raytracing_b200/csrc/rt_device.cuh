@@ -275,81 +275,110 @@ RT_DEV void test_record(const SceneView& sc, uint32_t rec, V3 o, V3 d, Hit& best
 }
 
 // ---------------------------------------------------------------------------------
-// BVH traversal: cast_ray_bvh (shader.wgsl:469-564) in the reference's visiting order
-// (near child chosen by the sign of inv_dir[split_axis]). Two result-preserving
-// changes: the slab test's far bound starts at 1.001 x the closest hit so far instead
-// of INFINITY, and shadow rays (ANY_HIT) return at the first accepted hit.
+// Ray casting: cast_ray_bvh (shader.wgsl:469-564) in the reference's visiting order
+// (near child chosen by the sign of inv_dir[split_axis]) plus cast_ray's brute-force
+// fallback (shader.wgsl:583-598), as ONE routine so the intersection code exists once
+// per call site.
+//
+// Structure ("while-while"): every lane first walks interior nodes until it owns a
+// pending leaf, then all lanes test their leaf primitives together; the fallback list
+// (all spheres, then all planes, stored behind the leaf slots) is handed to the same
+// primitive loop as a last virtual leaf when the BVH found nothing.
+//
+// Result-preserving changes versus the literal shader:
+//   * the slab test's far bound starts at 1.001 x the closest hit so far instead of
+//     INFINITY (closest-hit pruning);
+//   * any_hit (shadow rays) returns at the first accepted hit;
+//   * when no component of 1/d is infinite a slab can never produce NaN, so the
+//     swap/compare form reduces to min/max; rays with an infinite component take the
+//     literal select form, which keeps NaN slabs inert exactly like the WGSL.
 // `stack` is caller-provided storage with capacity >= the tree depth.
 // ---------------------------------------------------------------------------------
-template <bool ANY_HIT, bool COUNT, typename StackT>
-RT_DEV void traverse(const SceneView& sc, V3 o, V3 d, Hit& best, StackT stack, Counts& cn) {
-    V3 inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+#define RT_NONE 0xFFFFFFFFu
+
+#ifndef RT_TRACE_QUAL
+#define RT_TRACE_QUAL __device__ __noinline__
+#endif
+template <bool COUNT>
+RT_TRACE_QUAL void trace(const SceneView& sc, V3 o, V3 d, bool any_hit, bool with_fallback,
+                         Hit& best, uint32_t* stack, Counts& cn) {
+    const V3 inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    // "finite" is false for +-inf and NaN.
+    const bool plain = fabsf(inv.x) < 3.0e38f && fabsf(inv.y) < 3.0e38f && fabsf(inv.z) < 3.0e38f;
     best.t = RT_INFINITY;
-    best.rec = 0xFFFFFFFFu;
+    best.rec = RT_NONE;
     best.u = 0.0f;
     best.v = 0.0f;
     float limit = RT_INFINITY;
     uint32_t sp = 0u;
     uint32_t cur = 0u;
-    for (;;) {
-        float4 n0 = ld4(sc.nodes + 2u * (size_t)cur);
-        float4 n1 = ld4(sc.nodes + 2u * (size_t)cur + 1);
-        if (COUNT) cn.nodes++;
-        // ray_intersects_bounds (shader.wgsl:262-293); select-form swap keeps NaN slabs inert.
-        float t0 = 0.0f, t1 = limit;
-        {
-            float tn = (n0.x - o.x) * inv.x, tf = (n1.x - o.x) * inv.x;
-            bool sw = tn > tf;
-            float nr = sw ? tf : tn, fr = sw ? tn : tf;
-            t0 = nr > t0 ? nr : t0;
-            t1 = fr < t1 ? fr : t1;
-        }
-        {
-            float tn = (n0.y - o.y) * inv.y, tf = (n1.y - o.y) * inv.y;
-            bool sw = tn > tf;
-            float nr = sw ? tf : tn, fr = sw ? tn : tf;
-            t0 = nr > t0 ? nr : t0;
-            t1 = fr < t1 ? fr : t1;
-        }
-        {
-            float tn = (n0.z - o.z) * inv.z, tf = (n1.z - o.z) * inv.z;
-            bool sw = tn > tf;
-            float nr = sw ? tf : tn, fr = sw ? tn : tf;
-            t0 = nr > t0 ? nr : t0;
-            t1 = fr < t1 ? fr : t1;
-        }
-        if (!(t0 > t1)) {
-            uint32_t idx = __float_as_uint(n0.w);
-            uint32_t meta = __float_as_uint(n1.w);
-            uint32_t len = meta & 0x3FFFFFFFu;
-            if (len > 0u) {
-                for (uint32_t i = 0; i < len; i++) {
-                    test_record<COUNT>(sc, idx + i, o, d, best, cn);
-                    if (ANY_HIT && best.rec != 0xFFFFFFFFu) return;
-                }
-                limit = fminf(RT_INFINITY, best.t * 1.001f);
-            } else {
-                uint32_t axis = meta >> 30;
-                bool second_first = comp(inv, axis) < 0.0f;
-                stack[sp++] = second_first ? cur + 1u : idx;
-                cur = second_first ? idx : cur + 1u;
-                continue;
-            }
-        }
-        if (sp == 0u) break;
-        cur = stack[--sp];
-    }
-}
+    uint32_t leaf_begin = 0u, leaf_end = 0u;
+    bool fallback = with_fallback && (sc.sphere_count + sc.plane_count) > 0u;
 
-// cast_ray (shader.wgsl:567-601): BVH first; on a miss, brute-force every sphere then
-// every plane (triangles are not retried).
-template <bool COUNT, typename StackT>
-RT_DEV void cast_ray(const SceneView& sc, V3 o, V3 d, Hit& best, StackT stack, Counts& cn) {
-    traverse<false, COUNT>(sc, o, d, best, stack, cn);
-    if (best.rec != 0xFFFFFFFFu) return;
-    if (COUNT) cn.fallback++;
-    uint32_t n = sc.sphere_count + sc.plane_count;
-    for (uint32_t i = 0; i < n; i++) test_record<COUNT>(sc, sc.slot_count + i, o, d, best, cn);
+    for (;;) {
+        // ---- phase A: descend until this lane holds a leaf or has run out of nodes ----
+        while (cur != RT_NONE && leaf_begin == leaf_end) {
+            const float4 n0 = ld4(sc.nodes + 2u * (size_t)cur);
+            const float4 n1 = ld4(sc.nodes + 2u * (size_t)cur + 1);
+            if (COUNT) cn.nodes++;
+            // ray_intersects_bounds (shader.wgsl:262-293)
+            float tnx = (n0.x - o.x) * inv.x, tfx = (n1.x - o.x) * inv.x;
+            float tny = (n0.y - o.y) * inv.y, tfy = (n1.y - o.y) * inv.y;
+            float tnz = (n0.z - o.z) * inv.z, tfz = (n1.z - o.z) * inv.z;
+            float t0, t1;
+            if (plain) {
+                t0 = fmaxf(fmaxf(0.0f, fminf(tnx, tfx)), fmaxf(fminf(tny, tfy), fminf(tnz, tfz)));
+                t1 = fminf(fminf(limit, fmaxf(tnx, tfx)), fminf(fmaxf(tny, tfy), fmaxf(tnz, tfz)));
+            } else {
+                t0 = 0.0f;
+                t1 = limit;
+                bool sw = tnx > tfx;
+                float nr = sw ? tfx : tnx, fr = sw ? tnx : tfx;
+                t0 = nr > t0 ? nr : t0;
+                t1 = fr < t1 ? fr : t1;
+                sw = tny > tfy;
+                nr = sw ? tfy : tny, fr = sw ? tny : tfy;
+                t0 = nr > t0 ? nr : t0;
+                t1 = fr < t1 ? fr : t1;
+                sw = tnz > tfz;
+                nr = sw ? tfz : tnz, fr = sw ? tnz : tfz;
+                t0 = nr > t0 ? nr : t0;
+                t1 = fr < t1 ? fr : t1;
+            }
+            uint32_t next = RT_NONE;  // where to go if this node yields nothing to descend into
+            if (!(t0 > t1)) {
+                const uint32_t idx = __float_as_uint(n0.w);
+                const uint32_t meta = __float_as_uint(n1.w);
+                const uint32_t len = meta & 0x3FFFFFFFu;
+                if (len > 0u) {
+                    leaf_begin = idx;
+                    leaf_end = idx + len;
+                } else {
+                    const bool second_first = comp(inv, meta >> 30) < 0.0f;
+                    stack[sp++] = second_first ? cur + 1u : idx;
+                    next = second_first ? idx : cur + 1u;
+                }
+            }
+            if (next == RT_NONE && sp > 0u) next = stack[--sp];
+            cur = next;
+        }
+        if (leaf_begin == leaf_end) {
+            // BVH exhausted. cast_ray falls back to brute force only when nothing was hit.
+            if (!fallback || best.rec != RT_NONE) break;
+            fallback = false;
+            if (COUNT) cn.fallback++;
+            leaf_begin = sc.slot_count;
+            leaf_end = sc.slot_count + sc.sphere_count + sc.plane_count;
+        }
+        // ---- phase B: test the pending primitives ----
+        while (leaf_begin < leaf_end) {
+            test_record<COUNT>(sc, leaf_begin, o, d, best, cn);
+            leaf_begin++;
+            if (any_hit && best.rec != RT_NONE) return;
+        }
+        leaf_begin = leaf_end = 0u;
+        limit = fminf(RT_INFINITY, best.t * 1.001f);
+    }
 }
 
 // Deferred hit reconstruction: hit_point, shading normal, material row.
@@ -408,7 +437,7 @@ RT_DEV V3 env_bilinear(const EnvView& env, float u, float v) {
     float x0f = floorf(fx), y0f = floorf(fy);
     float wx = fx - x0f, wy = fy - y0f;
     float xmax = (float)(env.width - 1u), ymax = (float)(env.height - 1u);
-    // clamp to [0, size-1]; the !(f > 0) form sends NaN to 0 like the oracle.
+    // clamp to [0, size-1]; the !(f > 0) form sends NaN to 0 (arithmetic contract).
     float x0 = !(x0f > 0.0f) ? 0.0f : (x0f >= xmax ? xmax : x0f);
     float x1f = x0f + 1.0f;
     float x1 = !(x1f > 0.0f) ? 0.0f : (x1f >= xmax ? xmax : x1f);

@@ -76,6 +76,8 @@ def env_2k(rt):
 
 
 @pytest.fixture(scope="session")
-def cuda_available():
-    import torch
-    return torch.cuda.is_available()
+def cuda_available(rt):
+    import ctypes
+    n = ctypes.c_int(0)
+    rt._ffi.backend_lib().rt_device_count(ctypes.byref(n))
+    return n.value > 0

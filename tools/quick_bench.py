@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""Quick kernel timing for tuning: house.toml 1080p, given spp; prints ms, Mrays/s and an
+md5 of the accumulation buffer (all build variants must print the same hash).
+usage: RT_BACKEND_LIB=path tools/quick_bench.py [spp] [reps] [scene] [w] [h]"""
+import hashlib
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import _pkg
+
+rt = _pkg.load()
+spp = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+scene_name = sys.argv[3] if len(sys.argv) > 3 else "house"
+w = int(sys.argv[4]) if len(sys.argv) > 4 else 1920
+h = int(sys.argv[5]) if len(sys.argv) > 5 else 1080
+scene = rt.Scene.load_toml(os.path.join(ROOT, "assets", "scenes", f"{scene_name}.toml"))
+env = rt.EnvironmentMaps([rt.Environment.synthetic(2048, 1024)])
+st = rt.State(scene, env, w, h, max_bounces=8)
+st.render_samples(2)  # warm-up
+st.sync()
+best = 1e30
+for _ in range(reps):
+    st.reset()
+    st.reset_counters()
+    st.timer_start()
+    st.render_samples(spp)
+    ms = st.timer_stop()
+    best = min(best, ms)
+c = st.counters()
+rays = c["rays"] + c["shadow_rays"]
+digest = hashlib.md5(st.read_accum().tobytes()).hexdigest()[:12]
+print(f"{os.path.basename(os.environ.get('RT_BACKEND_LIB', 'default')):16} {scene_name} {w}x{h} spp={spp} "
+      f"best {best:9.3f} ms  {rays / best / 1e3:9.1f} Mrays/s  md5 {digest}")
