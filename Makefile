@@ -8,7 +8,7 @@ CXX      ?= g++
 NVCC     ?= /usr/local/cuda/bin/nvcc
 CUDA_HOME ?= /usr/local/cuda
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wextra -ffp-contract=off -fno-fast-math -Iinclude
-NVFLAGS  := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
+NVFLAGS  := $(EXTRA_NVFLAGS) -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
             --fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
             -Xcompiler -fPIC -Iinclude -Xptxas -v
 NCCL_INC ?= /usr/include

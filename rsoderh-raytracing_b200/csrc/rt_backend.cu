@@ -10,6 +10,9 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <time.h>
+#include <unistd.h>
+
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -19,6 +22,7 @@
 
 #include "rt_backend.h"
 #include "rt_device.cuh"
+#include "rt_pool.cuh"
 
 using namespace rtd;
 
@@ -282,6 +286,14 @@ __global__ void bake_materials_kernel(const float* src, float4* dst, uint32_t co
     if (i < count) bake_material(src + 12u * (size_t)i, dst + 3u * (size_t)i);
 }
 
+// max_bounces == 0: trace_ray's loop body never runs (shader.wgsl:1220); each sample adds 0.
+__global__ void zero_bounce_kernel(float4* accum, size_t count, unsigned long long* counters,
+                                   uint32_t samples) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) accum[i].w = 1.0f;
+    if (i == 0) atomicAdd(counters, (unsigned long long)count * samples);
+}
+
 __global__ void clear_accum_kernel(float4* accum, size_t count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) accum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -350,6 +362,7 @@ struct RtContext {
     float4* d_materials = nullptr;
     SceneView scene{};
     uint32_t bvh_depth = 0;
+    uint32_t node_count = 0, record_count = 0, material_count = 0;
     bool has_scene = false;
 
     // environments
@@ -369,6 +382,12 @@ struct RtContext {
     float4* d_accum = nullptr;
 
     unsigned long long* d_counters = nullptr;
+    uint32_t* d_next_pixel = nullptr;
+    uint32_t* d_stack_scratch = nullptr;  // only for BVHs deeper than the shared-memory stacks
+    int sm_count = 0;
+    bool use_pool = true;
+    bool pool_launched = false;
+    uint32_t* hb_host = nullptr;
     bool detailed = false;
     uint64_t launches = 0;
 };
@@ -451,7 +470,7 @@ bool validate_bvh(const RtSceneDesc& s, uint32_t* depth_out, std::string* why) {
                 *why = "BVH leaf primitive range out of range";
                 return false;
             }
-            if (n.primitives_len > 0x3FFFFFFFu) {
+            if (n.primitives_len > 0x1FFFFFFFu) {
                 *why = "BVH leaf too large";
                 return false;
             }
@@ -488,6 +507,18 @@ cudaError_t launch_first_hit(const FirstHitParams& p, uint32_t depth, cudaStream
     else if (depth <= 32) first_hit_kernel<COUNT, 32><<<grid, block, 0, stream>>>(p);
     else first_hit_kernel<COUNT, 64><<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
+}
+
+// After a synchronisation point: did the pool kernel's watchdog trip?
+int check_pool_status(RtContext* ctx) {
+    if (!ctx->pool_launched) return RT_OK;
+    uint32_t words[8] = {0};
+    cudaError_t e = cudaMemcpy(words, ctx->d_next_pixel, sizeof words, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
+    if (words[1] != 0u)
+        return fail(ctx, RT_ERR_CUDA, "render kernel watchdog tripped (code 0x%x: %u %u %u)", words[1],
+                    words[2], words[3], words[4]);
+    return RT_OK;
 }
 
 int check_ready(RtContext* ctx, uint32_t env_index, bool need_env) {
@@ -545,6 +576,16 @@ int rt_create(int device, RtContext** out) {
         return bail("cudaMalloc(counters)", e);
     if ((e = cudaMemset(ctx->d_counters, 0, sizeof(RtCounters))) != cudaSuccess)
         return bail("cudaMemset(counters)", e);
+    if ((e = cudaMalloc(&ctx->d_next_pixel, 8 * sizeof(uint32_t))) != cudaSuccess)
+        return bail("cudaMalloc(work counter)", e);
+    if ((e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
+        return bail("cudaDeviceGetAttribute", e);
+    if ((e = cudaFuncSetAttribute(rtp::render_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)rtp::pool_smem_bytes())) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(rtp::render_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)rtp::pool_smem_bytes())) != cudaSuccess)
+        return bail("cudaFuncSetAttribute(shared memory)", e);
+    if (const char* k = getenv("RT_KERNEL")) ctx->use_pool = strcmp(k, "pixel") != 0;
     *out = ctx;
     return RT_OK;
 }
@@ -557,6 +598,8 @@ void rt_destroy(RtContext* ctx) {
     free_envs(ctx);
     cudaFree(ctx->d_accum_own);
     cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_next_pixel);
+    cudaFree(ctx->d_stack_scratch);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -592,7 +635,13 @@ int rt_upload_scene(RtContext* ctx, const RtSceneDesc* s) {
     std::vector<float4> nodes((size_t)s->bvh_node_count * 2);
     for (uint32_t i = 0; i < s->bvh_node_count; i++) {
         const RtBvhNode& n = s->bvh_nodes[i];
-        uint32_t meta = n.primitives_len > 0 ? n.primitives_len : (n.split_axis << 30);
+        uint32_t meta = n.split_axis << 30;
+        if (n.primitives_len > 0) {
+            meta = n.primitives_len;
+            for (uint32_t k = 0; k < n.primitives_len; k++)
+                if (s->primitives[n.primitives_or_second_child_index + k].primitive_type != 2u)
+                    meta |= 0x20000000u;  // leaf holds a sphere or plane
+        }
         nodes[2 * (size_t)i] = make_float4(n.min[0], n.min[1], n.min[2], bits(n.primitives_or_second_child_index));
         nodes[2 * (size_t)i + 1] = make_float4(n.max[0], n.max[1], n.max[2], bits(meta));
     }
@@ -690,6 +739,14 @@ int rt_upload_scene(RtContext* ctx, const RtSceneDesc* s) {
     ctx->scene.sphere_count = s->sphere_count;
     ctx->scene.plane_count = s->plane_count;
     ctx->bvh_depth = depth;
+    ctx->node_count = s->bvh_node_count;
+    ctx->record_count = (uint32_t)rec_count;
+    ctx->material_count = s->material_count;
+    cudaFree(ctx->d_stack_scratch);
+    ctx->d_stack_scratch = nullptr;
+    if (depth > rtp::kSmemStack)
+        RT_CUDA(ctx, cudaMalloc(&ctx->d_stack_scratch,
+                                (size_t)ctx->sm_count * rtp::kSlots * rtp::kGlobalStack * sizeof(uint32_t)));
     ctx->has_scene = true;
     return RT_OK;
 }
@@ -800,23 +857,79 @@ int rt_render(RtContext* ctx, uint32_t sample_begin, uint32_t sample_count, uint
     if ((uint64_t)sample_begin + sample_count > 0xFFFFFFFFull)
         return fail(ctx, RT_ERR_INVALID_ARGUMENT, "sample range overflows u32");
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
-    RenderParams p;
-    p.scene = ctx->scene;
     const RtContext::Env& e = ctx->envs[env_index];
-    p.env.texture = e.texture;
-    p.env.alias = e.d_alias;
-    p.env.width = e.width;
-    p.env.height = e.height;
-    p.camera = ctx->camera;
-    p.accum = ctx->d_accum;
-    p.counters = ctx->d_counters;
-    p.width = ctx->width;
-    p.height = ctx->height;
-    p.sample_begin = sample_begin;
-    p.sample_count = sample_count;
-    p.max_bounces = max_bounces;
-    cudaError_t e2 = ctx->detailed ? launch_render<true>(p, ctx->bvh_depth, ctx->stream)
-                                   : launch_render<false>(p, ctx->bvh_depth, ctx->stream);
+    cudaError_t e2;
+    if (max_bounces == 0u) {
+        // No ray is ever cast: every sample adds zero radiance and writes alpha = 1.
+        size_t count = (size_t)ctx->width * ctx->height;
+        zero_bounce_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->d_accum, count, ctx->d_counters, sample_count);
+        e2 = cudaGetLastError();
+    } else if (ctx->use_pool) {
+        rtp::PoolParams p;
+        p.scene = ctx->scene;
+        p.env.texture = e.texture;
+        p.env.alias = e.d_alias;
+        p.env.width = e.width;
+        p.env.height = e.height;
+        p.camera = ctx->camera;
+        p.accum = ctx->d_accum;
+        p.counters = ctx->d_counters;
+        p.next_pixel = ctx->d_next_pixel;
+        p.stack_scratch = ctx->d_stack_scratch;
+        p.width = ctx->width;
+        p.height = ctx->height;
+        p.tiles_x = (ctx->width + 7u) / 8u;
+        p.pixel_ids = p.tiles_x * ((ctx->height + 7u) / 8u) * 64u;
+        p.sample_begin = sample_begin;
+        p.sample_count = sample_count;
+        p.max_bounces = max_bounces;
+        p.heartbeat = nullptr;
+#ifdef RT_POOL_DEBUG
+        {
+            static uint32_t* hb_host = nullptr;
+            static uint32_t* hb_dev = nullptr;
+            if (!hb_host) {
+                cudaHostAlloc(&hb_host, 64 * 64 * 4, cudaHostAllocMapped);
+                cudaHostGetDevicePointer(&hb_dev, hb_host, 0);
+            }
+            memset(hb_host, 0, 64 * 64 * 4);
+            p.heartbeat = hb_dev;
+            ctx->hb_host = hb_host;
+        }
+#endif
+        p.node_count = ctx->node_count;
+        p.record_count = ctx->record_count;
+        p.material_count = ctx->material_count;
+        RT_CUDA(ctx, cudaMemsetAsync(ctx->d_next_pixel, 0, 8 * sizeof(uint32_t), ctx->stream));
+        ctx->pool_launched = true;
+        // One persistent block per SM; fewer when the frame has fewer pixels than slots.
+        uint32_t pixels = ctx->width * ctx->height;
+        uint32_t blocks = (pixels + rtp::kSlots - 1) / rtp::kSlots;
+        if (blocks > (uint32_t)ctx->sm_count) blocks = (uint32_t)ctx->sm_count;
+        if (ctx->detailed)
+            rtp::render_pool_kernel<true><<<blocks, rtp::kThreads, rtp::pool_smem_bytes(), ctx->stream>>>(p);
+        else
+            rtp::render_pool_kernel<false><<<blocks, rtp::kThreads, rtp::pool_smem_bytes(), ctx->stream>>>(p);
+        e2 = cudaGetLastError();
+    } else {
+        RenderParams p;
+        p.scene = ctx->scene;
+        p.env.texture = e.texture;
+        p.env.alias = e.d_alias;
+        p.env.width = e.width;
+        p.env.height = e.height;
+        p.camera = ctx->camera;
+        p.accum = ctx->d_accum;
+        p.counters = ctx->d_counters;
+        p.width = ctx->width;
+        p.height = ctx->height;
+        p.sample_begin = sample_begin;
+        p.sample_count = sample_count;
+        p.max_bounces = max_bounces;
+        e2 = ctx->detailed ? launch_render<true>(p, ctx->bvh_depth, ctx->stream)
+                           : launch_render<false>(p, ctx->bvh_depth, ctx->stream);
+    }
     ctx->launches++;
     if (e2 != cudaSuccess)
         return fail(ctx, RT_ERR_CUDA, "render kernel launch failed: %s", cudaGetErrorString(e2));
@@ -865,8 +978,36 @@ int rt_first_hit(RtContext* ctx, uint32_t sample_index, uint32_t* slot_out, floa
 int rt_sync(RtContext* ctx) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
+#ifdef RT_POOL_DEBUG
+    if (ctx->hb_host) {
+        for (int ms = 0; ms < 5000 && cudaStreamQuery(ctx->stream) == cudaErrorNotReady; ms++) {
+            struct timespec ts = {0, 1000000};
+            nanosleep(&ts, nullptr);
+        }
+        cudaError_t qe = cudaStreamQuery(ctx->stream);
+        if (qe != cudaSuccess) {
+            fprintf(stderr, "stream state: %s\n", cudaGetErrorString(qe));
+            for (int b = 0; b < 64; b++) {
+                bool quiet = true;
+                for (int w = 0; w < 16; w++) if (ctx->hb_host[b * 64 + 2 * w + 1] != 0u) quiet = false;
+                for (int q = 0; q < 7; q++) if (ctx->hb_host[b * 64 + 40 + 2 * q] != ctx->hb_host[b * 64 + 41 + 2 * q]) quiet = false;
+                if (quiet) { fprintf(stderr, "block %d quiet (it0=%u)\n", b, ctx->hb_host[b * 64]); continue; }
+                fprintf(stderr, "block %d heartbeat:", b);
+                for (int w = 0; w < 16; w++)
+                    fprintf(stderr, " [w%d it=%u %08x]", w, ctx->hb_host[b * 64 + 2 * w],
+                            ctx->hb_host[b * 64 + 2 * w + 1]);
+                fprintf(stderr, "\n  queues wr/rd:");
+                for (int q = 0; q < 7; q++)
+                    fprintf(stderr, " %u/%u", ctx->hb_host[b * 64 + 40 + 2 * q], ctx->hb_host[b * 64 + 41 + 2 * q]);
+                fprintf(stderr, "\n");
+            }
+            fflush(stderr);
+            _exit(3);
+        }
+    }
+#endif
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return RT_OK;
+    return check_pool_status(ctx);
 }
 
 int rt_read_accum(RtContext* ctx, float* rgba_out) {
@@ -878,7 +1019,7 @@ int rt_read_accum(RtContext* ctx, float* rgba_out) {
                                  (size_t)ctx->width * ctx->height * sizeof(float4),
                                  cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return RT_OK;
+    return check_pool_status(ctx);
 }
 
 int rt_write_accum(RtContext* ctx, const float* rgba_in) {

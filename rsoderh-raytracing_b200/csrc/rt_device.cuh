@@ -140,7 +140,8 @@ RT_DEV uint32_t rng_seed(uint32_t pixel_index, uint32_t sample_count) {
 
 // ---------------------------------------------------------------------------------
 // Device scene view. Records are 128-bit aligned and read with vector loads.
-//   nodes:   2 x float4 per node : (min.xyz, bits idx) (max.xyz, bits len | axis << 30)
+//   nodes:   2 x float4 per node : (min.xyz, bits idx) (max.xyz, bits meta); meta = len (29 bits)
+//            | bit 29 set when the leaf holds a sphere or plane | split axis << 30
 //   records: 4 x float4 per primitive, indexed by leaf slot, followed by the brute-force
 //            fallback lists (all spheres, then all planes) in reference order:
 //     triangle (type 2): (a.xyz, type) (e0.xyz, mat) (e1.xyz, -) (-)
@@ -349,7 +350,7 @@ RT_TRACE_QUAL void trace(const SceneView& sc, V3 o, V3 d, bool any_hit, bool wit
             if (!(t0 > t1)) {
                 const uint32_t idx = __float_as_uint(n0.w);
                 const uint32_t meta = __float_as_uint(n1.w);
-                const uint32_t len = meta & 0x3FFFFFFFu;
+                const uint32_t len = meta & 0x1FFFFFFFu;
                 if (len > 0u) {
                     leaf_begin = idx;
                     leaf_end = idx + len;
