@@ -387,7 +387,6 @@ struct RtContext {
     int sm_count = 0;
     bool use_pool = true;
     bool pool_launched = false;
-    uint32_t* hb_host = nullptr;
     bool detailed = false;
     uint64_t launches = 0;
 };
@@ -884,20 +883,6 @@ int rt_render(RtContext* ctx, uint32_t sample_begin, uint32_t sample_count, uint
         p.sample_begin = sample_begin;
         p.sample_count = sample_count;
         p.max_bounces = max_bounces;
-        p.heartbeat = nullptr;
-#ifdef RT_POOL_DEBUG
-        {
-            static uint32_t* hb_host = nullptr;
-            static uint32_t* hb_dev = nullptr;
-            if (!hb_host) {
-                cudaHostAlloc(&hb_host, 64 * 64 * 4, cudaHostAllocMapped);
-                cudaHostGetDevicePointer(&hb_dev, hb_host, 0);
-            }
-            memset(hb_host, 0, 64 * 64 * 4);
-            p.heartbeat = hb_dev;
-            ctx->hb_host = hb_host;
-        }
-#endif
         p.node_count = ctx->node_count;
         p.record_count = ctx->record_count;
         p.material_count = ctx->material_count;
@@ -978,34 +963,6 @@ int rt_first_hit(RtContext* ctx, uint32_t sample_index, uint32_t* slot_out, floa
 int rt_sync(RtContext* ctx) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
-#ifdef RT_POOL_DEBUG
-    if (ctx->hb_host) {
-        for (int ms = 0; ms < 5000 && cudaStreamQuery(ctx->stream) == cudaErrorNotReady; ms++) {
-            struct timespec ts = {0, 1000000};
-            nanosleep(&ts, nullptr);
-        }
-        cudaError_t qe = cudaStreamQuery(ctx->stream);
-        if (qe != cudaSuccess) {
-            fprintf(stderr, "stream state: %s\n", cudaGetErrorString(qe));
-            for (int b = 0; b < 64; b++) {
-                bool quiet = true;
-                for (int w = 0; w < 16; w++) if (ctx->hb_host[b * 64 + 2 * w + 1] != 0u) quiet = false;
-                for (int q = 0; q < 7; q++) if (ctx->hb_host[b * 64 + 40 + 2 * q] != ctx->hb_host[b * 64 + 41 + 2 * q]) quiet = false;
-                if (quiet) { fprintf(stderr, "block %d quiet (it0=%u)\n", b, ctx->hb_host[b * 64]); continue; }
-                fprintf(stderr, "block %d heartbeat:", b);
-                for (int w = 0; w < 16; w++)
-                    fprintf(stderr, " [w%d it=%u %08x]", w, ctx->hb_host[b * 64 + 2 * w],
-                            ctx->hb_host[b * 64 + 2 * w + 1]);
-                fprintf(stderr, "\n  queues wr/rd:");
-                for (int q = 0; q < 7; q++)
-                    fprintf(stderr, " %u/%u", ctx->hb_host[b * 64 + 40 + 2 * q], ctx->hb_host[b * 64 + 41 + 2 * q]);
-                fprintf(stderr, "\n");
-            }
-            fflush(stderr);
-            _exit(3);
-        }
-    }
-#endif
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return check_pool_status(ctx);
 }

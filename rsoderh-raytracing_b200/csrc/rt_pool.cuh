@@ -13,8 +13,8 @@
 //   SHADE    closest hit found: material, next-event estimation set-up, BSDF sample
 //   SKY      ray escaped: environment radiance with MIS weight
 //   CONTINUE apply the shadow-ray result and start the next bounce
-//   LEAF_*   test the primitives of the pending leaf (triangle-only leaves apart)
-//   NODE     walk up to kNodeSteps BVH nodes, stop at the first leaf whose box is hit
+//   TRAVERSE resume the ray's BVH walk for up to kNodeBudget node tests (while-while:
+//            descend to a leaf, test its primitives, repeat), brute-force fallback included
 //
 // A slot is in exactly one queue (or inside one warp) at any time. A pixel is owned by one
 // slot for all of its samples, which are traced in sample order, so the accumulation order
@@ -33,22 +33,18 @@ using namespace rtd;
 #ifndef RT_POOL_THREADS
 #define RT_POOL_THREADS 512
 #endif
-#ifndef RT_NODE_STEPS
-#define RT_NODE_STEPS 4
-#endif
-#ifndef RT_LEAF_PRIMS
-#define RT_LEAF_PRIMS 4
+#ifndef RT_NODE_BUDGET
+#define RT_NODE_BUDGET 12
 #endif
 
 constexpr uint32_t kSlots = RT_POOL_SLOTS;  // power of two, <= 32768
 constexpr uint32_t kThreads = RT_POOL_THREADS;
-constexpr uint32_t kNodeSteps = RT_NODE_STEPS;
-constexpr uint32_t kLeafPrims = RT_LEAF_PRIMS;
+constexpr uint32_t kNodeBudget = RT_NODE_BUDGET;  // node tests per TRAVERSE visit
 constexpr uint32_t kSmemStack = 8;  // deeper trees keep their stacks in a global scratch buffer
 constexpr uint32_t kGlobalStack = 64;
 
-// Queue order = pick priority (expensive, rarely-full stages first; NODE is the reservoir).
-enum Stage : int { ST_FINISH = 0, ST_SHADE, ST_SKY, ST_CONTINUE, ST_LEAF_MIX, ST_LEAF_TRI, ST_NODE, ST_COUNT };
+// Queue order = scan priority (rarely-full stages first; TRAVERSE is the reservoir).
+enum Stage : int { ST_FINISH = 0, ST_SHADE, ST_SKY, ST_CONTINUE, ST_TRAVERSE, ST_COUNT };
 
 enum Field : uint32_t {
     F_OX, F_OY, F_OZ,   // ray origin
@@ -59,7 +55,7 @@ enum Field : uint32_t {
     F_LX, F_LY, F_LZ,   // radiance of the current sample
     F_PX, F_PY, F_PZ,   // pending next-event contribution (added if the shadow ray is free)
     F_RNG, F_PDF, F_PIXEL, F_SAMPLE, F_FLAGS,
-    F_CUR, F_SP, F_LB, F_LE,      // traversal cursor, stack size, pending leaf range
+    F_CUR, F_SP,                  // traversal cursor, stack size
     F_BT, F_BR, F_BU, F_BV,       // closest hit so far
     F_STACK,
     F_COUNT = F_STACK + kSmemStack
@@ -71,23 +67,6 @@ constexpr uint32_t FLAG_FB_DONE = 4u;   // brute-force fallback already run for 
 constexpr uint32_t FLAG_PLAIN = 8u;     // no component of 1/d is infinite
 constexpr uint32_t FLAG_OCCLUDED = 16u; // shadow ray hit something
 constexpr uint32_t FLAG_BOUNCE_SHIFT = 8u;
-
-#ifdef RT_POOL_DEBUG
-#define RT_POOL_CHECK(cond, code, a, b)                                        \
-    do {                                                                       \
-        if (!(cond)) {                                                         \
-            if (atomicCAS(pl.status, 0u, 0x1000u + (code)) == 0u) {            \
-                pl.status[1] = (uint32_t)(a);                                  \
-                pl.status[2] = (uint32_t)(b);                                  \
-                pl.status[3] = slot;                                           \
-            }                                                                  \
-            atomicSub((uint32_t*)pl.live, 1u);                                 \
-            return -1;                                                         \
-        }                                                                      \
-    } while (0)
-#else
-#define RT_POOL_CHECK(cond, code, a, b) do {} while (0)
-#endif
 
 // Ring queues: 2 * kSlots entries of 16 bits = slot (10 bits) | lap tag (6 bits). Producers
 // reserve a position with one atomicAdd and then store unconditionally (wait-free);
@@ -113,7 +92,6 @@ struct PoolParams {
     uint32_t sample_begin, sample_count;
     uint32_t max_bounces;
     uint32_t node_count, record_count, material_count;  // bounds for RT_POOL_DEBUG checks
-    volatile uint32_t* heartbeat;  // RT_POOL_DEBUG: mapped host memory, 64 words per block
 };
 
 constexpr size_t pool_smem_bytes() {
@@ -160,152 +138,150 @@ RT_DEV void begin_ray(Pool& pl, uint32_t slot, V3 d, uint32_t& flags) {
     flags = (flags & ~(FLAG_FB_DONE | FLAG_PLAIN | FLAG_OCCLUDED)) | (plain ? FLAG_PLAIN : 0u);
     pl.setu(F_CUR, slot, 0u);
     pl.setu(F_SP, slot, 0u);
-    pl.setu(F_LB, slot, 0u);
-    pl.setu(F_LE, slot, 0u);
     pl.setf(F_BT, slot, RT_INFINITY);
     pl.setu(F_BR, slot, RT_NONE);
     pl.setf(F_BU, slot, 0.0f);
     pl.setf(F_BV, slot, 0.0f);
 }
 
-// The BVH (and, for closest-hit rays, the fallback) is exhausted: where does the slot go?
-RT_DEV int route_done(const PoolParams& p, Pool& pl, uint32_t slot, uint32_t& flags, uint32_t best_rec,
-                      Counts& cn, bool count) {
-    if (flags & FLAG_SHADOW) return (flags & FLAG_ENDS) ? ST_FINISH : ST_CONTINUE;
-    if (best_rec != RT_NONE) return ST_SHADE;
-    uint32_t fb = p.scene.sphere_count + p.scene.plane_count;
-    if (!(flags & FLAG_FB_DONE) && fb > 0u) {
-        // cast_ray's brute-force loop (shader.wgsl:583-598) as a last virtual leaf.
-        flags |= FLAG_FB_DONE;
-        if (count) cn.fallback++;
-        pl.setu(F_LB, slot, p.scene.slot_count);
-        pl.setu(F_LE, slot, p.scene.slot_count + fb);
-        return ST_LEAF_MIX;
-    }
-    return ST_SKY;
-}
-
-// ---- NODE: ray_intersects_bounds + descent (shader.wgsl:262-293, 487-557) ----
+// ---- TRAVERSE: cast_ray_bvh (shader.wgsl:469-564) + cast_ray's fallback (583-598) ----
+// Same walk as rtd::trace (reference visiting order, closest-hit pruning, any-hit exit for
+// shadow rays, min/max slabs when 1/d is finite), made resumable: the cursor, stack and
+// closest hit live in the slot, and a visit ends after kNodeBudget node tests. Leaves are
+// always finished inside the visit that reached them.
 template <bool COUNT>
-RT_DEV int stage_node(const PoolParams& p, Pool& pl, uint32_t slot, Counts& cn) {
+RT_DEV int stage_traverse(const PoolParams& p, Pool& pl, uint32_t slot, Counts& cn) {
     const V3 o = pl.get3(F_OX, slot);
+    const V3 d = pl.get3(F_DX, slot);
     const V3 inv = pl.get3(F_IX, slot);
     uint32_t flags = pl.getu(F_FLAGS, slot);
     const bool plain = (flags & FLAG_PLAIN) != 0u;
+    const bool any_hit = (flags & FLAG_SHADOW) != 0u;
     uint32_t cur = pl.getu(F_CUR, slot);
     uint32_t sp = pl.getu(F_SP, slot);
-    const float limit = fminf(RT_INFINITY, pl.getf(F_BT, slot) * 1.001f);
-    int dest = ST_NODE;
-    for (uint32_t step = 0; step < kNodeSteps && cur != RT_NONE; step++) {
-        RT_POOL_CHECK(cur < p.node_count, 1, cur, sp);
-        RT_POOL_CHECK(sp < kSmemStack || pl.gstack, 2, cur, sp);
-        const float4 n0 = ld4(p.scene.nodes + 2u * (size_t)cur);
-        const float4 n1 = ld4(p.scene.nodes + 2u * (size_t)cur + 1);
-        if (COUNT) cn.nodes++;
-        float tnx = (n0.x - o.x) * inv.x, tfx = (n1.x - o.x) * inv.x;
-        float tny = (n0.y - o.y) * inv.y, tfy = (n1.y - o.y) * inv.y;
-        float tnz = (n0.z - o.z) * inv.z, tfz = (n1.z - o.z) * inv.z;
-        float t0, t1;
-        if (plain) {
-            t0 = fmaxf(fmaxf(0.0f, fminf(tnx, tfx)), fmaxf(fminf(tny, tfy), fminf(tnz, tfz)));
-            t1 = fminf(fminf(limit, fmaxf(tnx, tfx)), fminf(fmaxf(tny, tfy), fmaxf(tnz, tfz)));
-        } else {
-            t0 = 0.0f;
-            t1 = limit;
-            bool sw = tnx > tfx;
-            float nr = sw ? tfx : tnx, fr = sw ? tnx : tfx;
-            t0 = nr > t0 ? nr : t0;
-            t1 = fr < t1 ? fr : t1;
-            sw = tny > tfy;
-            nr = sw ? tfy : tny, fr = sw ? tny : tfy;
-            t0 = nr > t0 ? nr : t0;
-            t1 = fr < t1 ? fr : t1;
-            sw = tnz > tfz;
-            nr = sw ? tfz : tnz, fr = sw ? tnz : tfz;
-            t0 = nr > t0 ? nr : t0;
-            t1 = fr < t1 ? fr : t1;
-        }
-        uint32_t next = RT_NONE;
-        bool leaf = false;
-        if (!(t0 > t1)) {
-            const uint32_t idx = __float_as_uint(n0.w);
-            const uint32_t meta = __float_as_uint(n1.w);
-            const uint32_t len = meta & 0x1FFFFFFFu;
-            if (len > 0u) {
-                leaf = true;
-                pl.setu(F_LB, slot, idx);
-                pl.setu(F_LE, slot, idx + len);
-                dest = (meta & 0x20000000u) ? ST_LEAF_MIX : ST_LEAF_TRI;
-            } else {
-                const bool second_first = comp(inv, meta >> 30) < 0.0f;
-                pl.stack_push(slot, sp, second_first ? cur + 1u : idx);
-                sp++;
-                next = second_first ? idx : cur + 1u;
-            }
-        }
-        if (next == RT_NONE && sp > 0u) {
-            sp--;
-            next = pl.stack_pop(slot, sp);
-        }
-        cur = next;
-        if (leaf) break;
-    }
-    pl.setu(F_CUR, slot, cur);
-    pl.setu(F_SP, slot, sp);
-    if (dest == ST_NODE && cur == RT_NONE) {
-        dest = route_done(p, pl, slot, flags, pl.getu(F_BR, slot), cn, COUNT);
-        pl.setu(F_FLAGS, slot, flags);
-    }
-    return dest;
-}
-
-// ---- LEAF: primitive tests of the pending leaf (shader.wgsl:493-524) ----
-template <bool COUNT, bool TRI_ONLY>
-RT_DEV int stage_leaf(const PoolParams& p, Pool& pl, uint32_t slot, Counts& cn) {
-    const V3 o = pl.get3(F_OX, slot);
-    const V3 d = pl.get3(F_DX, slot);
-    uint32_t flags = pl.getu(F_FLAGS, slot);
     Hit best;
     best.t = pl.getf(F_BT, slot);
     best.rec = pl.getu(F_BR, slot);
     best.u = pl.getf(F_BU, slot);
     best.v = pl.getf(F_BV, slot);
-    uint32_t lb = pl.getu(F_LB, slot);
-    const uint32_t le = pl.getu(F_LE, slot);
-    const bool any_hit = (flags & FLAG_SHADOW) != 0u;
-    RT_POOL_CHECK(le <= p.record_count && lb <= le, 3, lb, le);
-    for (uint32_t i = 0; i < kLeafPrims && lb < le; i++) {
-        if (TRI_ONLY) {
-            const float4* r = p.scene.records + 4u * (size_t)lb;
-            float4 r0 = ld4(r), r1 = ld4(r + 1), r2 = ld4(r + 2);
-            float t = 0.0f, u = 0.0f, v = 0.0f;
-            if (COUNT) cn.tris++;
-            if (test_triangle(o, d, r0, r1, r2, t, u, v) && t < best.t) {
-                best.t = t;
-                best.rec = lb;
-                best.u = u;
-                best.v = v;
+    float limit = fminf(RT_INFINITY, best.t * 1.001f);
+    uint32_t budget = kNodeBudget;
+    uint32_t leaf_begin = 0u, leaf_end = 0u;
+    bool leaf_mixed = false;
+
+    for (;;) {
+        // ---- phase A: descend until this lane holds a leaf, runs out of nodes or budget ----
+        while (cur != RT_NONE && leaf_begin == leaf_end && budget > 0u) {
+            budget--;
+            const float4 n0 = ld4(p.scene.nodes + 2u * (size_t)cur);
+            const float4 n1 = ld4(p.scene.nodes + 2u * (size_t)cur + 1);
+            if (COUNT) cn.nodes++;
+            float tnx = (n0.x - o.x) * inv.x, tfx = (n1.x - o.x) * inv.x;
+            float tny = (n0.y - o.y) * inv.y, tfy = (n1.y - o.y) * inv.y;
+            float tnz = (n0.z - o.z) * inv.z, tfz = (n1.z - o.z) * inv.z;
+            float t0, t1;
+            if (plain) {
+                t0 = fmaxf(fmaxf(0.0f, fminf(tnx, tfx)), fmaxf(fminf(tny, tfy), fminf(tnz, tfz)));
+                t1 = fminf(fminf(limit, fmaxf(tnx, tfx)), fminf(fmaxf(tny, tfy), fmaxf(tnz, tfz)));
+            } else {
+                t0 = 0.0f;
+                t1 = limit;
+                bool sw = tnx > tfx;
+                float nr = sw ? tfx : tnx, fr = sw ? tnx : tfx;
+                t0 = nr > t0 ? nr : t0;
+                t1 = fr < t1 ? fr : t1;
+                sw = tny > tfy;
+                nr = sw ? tfy : tny, fr = sw ? tny : tfy;
+                t0 = nr > t0 ? nr : t0;
+                t1 = fr < t1 ? fr : t1;
+                sw = tnz > tfz;
+                nr = sw ? tfz : tnz, fr = sw ? tnz : tfz;
+                t0 = nr > t0 ? nr : t0;
+                t1 = fr < t1 ? fr : t1;
+            }
+            uint32_t next = RT_NONE;
+            if (!(t0 > t1)) {
+                const uint32_t idx = __float_as_uint(n0.w);
+                const uint32_t meta = __float_as_uint(n1.w);
+                const uint32_t len = meta & 0x1FFFFFFFu;
+                if (len > 0u) {
+                    leaf_begin = idx;
+                    leaf_end = idx + len;
+                    leaf_mixed = (meta & 0x20000000u) != 0u;
+                } else {
+                    const bool second_first = comp(inv, meta >> 30) < 0.0f;
+                    pl.stack_push(slot, sp, second_first ? cur + 1u : idx);
+                    sp++;
+                    next = second_first ? idx : cur + 1u;
+                }
+            }
+            if (next == RT_NONE && sp > 0u) {
+                sp--;
+                next = pl.stack_pop(slot, sp);
+            }
+            cur = next;
+        }
+        if (leaf_begin == leaf_end) {
+            if (cur != RT_NONE) break;  // budget spent: suspend
+            // BVH exhausted. cast_ray falls back to brute force only when nothing was hit.
+            uint32_t fb = p.scene.sphere_count + p.scene.plane_count;
+            if (any_hit || best.rec != RT_NONE || (flags & FLAG_FB_DONE) || fb == 0u) break;
+            flags |= FLAG_FB_DONE;
+            if (COUNT) cn.fallback++;
+            leaf_begin = p.scene.slot_count;
+            leaf_end = p.scene.slot_count + fb;
+            leaf_mixed = true;
+        }
+        // ---- phase B: test the pending primitives ----
+        if (leaf_mixed) {
+            while (leaf_begin < leaf_end) {
+                test_record<COUNT>(p.scene, leaf_begin, o, d, best, cn);
+                leaf_begin++;
+                if (any_hit && best.rec != RT_NONE) break;
             }
         } else {
-            test_record<COUNT>(p.scene, lb, o, d, best, cn);
+            while (leaf_begin < leaf_end) {
+                const float4* r = p.scene.records + 4u * (size_t)leaf_begin;
+                float4 r0 = ld4(r), r1 = ld4(r + 1), r2 = ld4(r + 2);
+                float t = 0.0f, u = 0.0f, v = 0.0f;
+                if (COUNT) cn.tris++;
+                if (test_triangle(o, d, r0, r1, r2, t, u, v) && t < best.t) {
+                    best.t = t;
+                    best.rec = leaf_begin;
+                    best.u = u;
+                    best.v = v;
+                }
+                leaf_begin++;
+                if (any_hit && best.rec != RT_NONE) break;
+            }
         }
-        lb++;
         if (any_hit && best.rec != RT_NONE) {
-            // Occluded: the rest of the traversal cannot change the answer.
+            // Occluded: the rest of the walk cannot change the answer.
             pl.setu(F_FLAGS, slot, flags | FLAG_OCCLUDED);
             return (flags & FLAG_ENDS) ? ST_FINISH : ST_CONTINUE;
         }
+        leaf_begin = leaf_end = 0u;
+        limit = fminf(RT_INFINITY, best.t * 1.001f);
     }
+
+    if (cur != RT_NONE) {
+        // Suspended: park the walk in the slot and come back.
+        pl.setu(F_CUR, slot, cur);
+        pl.setu(F_SP, slot, sp);
+        pl.setf(F_BT, slot, best.t);
+        pl.setu(F_BR, slot, best.rec);
+        pl.setf(F_BU, slot, best.u);
+        pl.setf(F_BV, slot, best.v);
+        pl.setu(F_FLAGS, slot, flags);
+        return ST_TRAVERSE;
+    }
+    if (any_hit) return (flags & FLAG_ENDS) ? ST_FINISH : ST_CONTINUE;  // shadow ray is free
+    if (best.rec == RT_NONE) return ST_SKY;
     pl.setf(F_BT, slot, best.t);
     pl.setu(F_BR, slot, best.rec);
     pl.setf(F_BU, slot, best.u);
     pl.setf(F_BV, slot, best.v);
-    pl.setu(F_LB, slot, lb);
-    if (lb < le) return TRI_ONLY ? ST_LEAF_TRI : ST_LEAF_MIX;
-    if (pl.getu(F_CUR, slot) != RT_NONE) return ST_NODE;
-    int dest = route_done(p, pl, slot, flags, best.rec, cn, COUNT);
-    pl.setu(F_FLAGS, slot, flags);
-    return dest;
+    return ST_SHADE;
 }
 
 // ---- SKY: the ray escaped (shader.wgsl:1222-1231) ----
@@ -337,8 +313,6 @@ RT_DEV int stage_shade(const PoolParams& p, Pool& pl, uint32_t slot, Counts& cn)
     hit.rec = pl.getu(F_BR, slot);
     hit.u = pl.getf(F_BU, slot);
     hit.v = pl.getf(F_BV, slot);
-
-    RT_POOL_CHECK(hit.rec < p.record_count, 4, hit.rec, flags);
     V3 point, n;
     uint32_t mat_id;
     reconstruct_hit(p.scene, o, d, hit, point, n, mat_id);
@@ -348,7 +322,6 @@ RT_DEV int stage_shade(const PoolParams& p, Pool& pl, uint32_t slot, Counts& cn)
             __float_as_int(ld4(p.scene.records + 4u * (size_t)hit.rec).w) == 2)
             cn.tri_hits++;
     }
-    RT_POOL_CHECK(mat_id < p.material_count, 5, mat_id, hit.rec);
     const Material m = load_material(p.scene, mat_id);
     L = L + T * m.emission;  // shader.wgsl:1236
 
@@ -365,7 +338,6 @@ RT_DEV int stage_shade(const PoolParams& p, Pool& pl, uint32_t slot, Counts& cn)
         uint32_t index = min((uint32_t)(rng_uniform(rng) * (float)length), length - 1u);
         float4 entry = ld4(p.env.alias + index);
         uint32_t pick = rng_uniform(rng) < entry.x ? index : __float_as_uint(entry.y);
-        RT_POOL_CHECK(pick < length, 6, pick, index);
         uint32_t ex = pick % p.env.width, ey = pick / p.env.width;
         float jx = rng_uniform(rng), jy = rng_uniform(rng);
         float eu = ((float)ex + jx) / (float)p.env.width;
@@ -474,7 +446,7 @@ RT_DEV int stage_shade(const PoolParams& p, Pool& pl, uint32_t slot, Counts& cn)
         flags |= FLAG_SHADOW;
         pl.set3(F_PX, slot, pending);
         begin_ray(pl, slot, shadow_dir, flags);
-        dest = ST_NODE;
+        dest = ST_TRAVERSE;
     } else {
         dest = done ? ST_FINISH : ST_CONTINUE;
     }
@@ -498,7 +470,7 @@ RT_DEV int stage_continue(Pool& pl, uint32_t slot, Counts& cn) {
     cn.rays++;
     begin_ray(pl, slot, pl.get3(F_NX, slot), flags);
     pl.setu(F_FLAGS, slot, flags);
-    return ST_NODE;
+    return ST_TRAVERSE;
 }
 
 // 8x8-tile-major pixel enumeration: consecutive ids are spatially close.
@@ -516,7 +488,6 @@ RT_DEV int stage_finish(const PoolParams& p, Pool& pl, uint32_t slot, float sin_
     uint32_t pixel = pl.getu(F_PIXEL, slot);
     uint32_t sample = pl.getu(F_SAMPLE, slot);
     const uint32_t sample_end = p.sample_begin + p.sample_count;
-    RT_POOL_CHECK(pixel == kNoPixel || pixel < p.width * p.height, 7, pixel, sample);
     if (pixel != kNoPixel) {
         V3 L = pl.get3(F_LX, slot);
         float4 a = __ldcg(p.accum + pixel);
@@ -562,7 +533,7 @@ RT_DEV int stage_finish(const PoolParams& p, Pool& pl, uint32_t slot, float sin_
     flags = 0u;
     begin_ray(pl, slot, d, flags);
     pl.setu(F_FLAGS, slot, flags);
-    return ST_NODE;
+    return ST_TRAVERSE;
 }
 
 RT_DEV uint32_t ring_entry(uint32_t position, uint32_t slot) {
@@ -570,10 +541,13 @@ RT_DEV uint32_t ring_entry(uint32_t position, uint32_t slot) {
 }
 
 // Publishes every lane's slot to its destination queue (dest < 0: nothing to publish).
+// DEST_MASK lists the stages the stage just run can route to.
+template <uint32_t DEST_MASK>
 RT_DEV void publish(Pool& pl, int dest, uint32_t slot, uint32_t lane) {
     __threadfence_block();  // slot state before queue entry
 #pragma unroll
     for (int s = 0; s < ST_COUNT; s++) {
+        if (!(DEST_MASK & (1u << s))) continue;
         unsigned m = __ballot_sync(0xFFFFFFFFu, dest == s);
         if (m) {
             int leader = __ffs(m) - 1;
@@ -628,12 +602,14 @@ __global__ void __launch_bounds__(kThreads, 1) render_pool_kernel(const PoolPara
     memset(&cn, 0, sizeof cn);
     uint32_t idle = 0;
 
+    int sticky = ST_TRAVERSE;  // the stage this warp ran last: its code is hot in the I-cache
     for (;;) {
-        // ---- lane 0 decides for the warp: reserve a chunk (a full one from the first queue
-        //      that holds 32, else the largest partial one), idle, or leave. Every lane acts
+        // ---- lane 0 decides for the warp: reserve a chunk, idle, or leave. Every lane acts
         //      on the broadcast decision only: after a *_sync the lanes of a warp may still
         //      run as separate groups, so each reading `live` itself could split the warp
-        //      between "leave" and "stay". ----
+        //      between "leave" and "stay".
+        //      Choice: a full chunk (32) of the stage run last, else a full chunk of the first
+        //      queue in priority order, else the largest partial chunk. ----
         int stage = -1;  // >= 0 stage to run, -1 idle, -2 all slots retired, -3 abort
         uint32_t base = 0, n = 0;
         if (lane == 0) {
@@ -643,19 +619,30 @@ __global__ void __launch_bounds__(kThreads, 1) render_pool_kernel(const PoolPara
                 for (;;) {
                     int pick = -1;
                     uint32_t pick_avail = 0, pick_rd = 0;
-                    for (int s = 0; s < ST_COUNT; s++) {
-                        uint32_t r = pl.rd[s];
-                        uint32_t avail = pl.wr[s] - r;
+                    {
+                        uint32_t r = pl.rd[sticky];
+                        uint32_t avail = pl.wr[sticky] - r;
                         if (avail >= 32u) {
-                            pick = s;
+                            pick = sticky;
                             pick_avail = 32u;
                             pick_rd = r;
-                            break;
                         }
-                        if (avail > pick_avail) {
-                            pick = s;
-                            pick_avail = avail;
-                            pick_rd = r;
+                    }
+                    if (pick < 0) {
+                        for (int s = 0; s < ST_COUNT; s++) {
+                            uint32_t r = pl.rd[s];
+                            uint32_t avail = pl.wr[s] - r;
+                            if (avail >= 32u) {
+                                pick = s;
+                                pick_avail = 32u;
+                                pick_rd = r;
+                                break;
+                            }
+                            if (avail > pick_avail) {
+                                pick = s;
+                                pick_avail = avail;
+                                pick_rd = r;
+                            }
                         }
                     }
                     if (pick < 0) break;
@@ -683,17 +670,6 @@ __global__ void __launch_bounds__(kThreads, 1) render_pool_kernel(const PoolPara
                 }
             }
         }
-#ifdef RT_POOL_DEBUG
-        if (lane == 0 && p.heartbeat && blockIdx.x < 64) {
-            volatile uint32_t* hb = p.heartbeat + blockIdx.x * 64 + (threadIdx.x >> 5) * 2;
-            hb[0] = hb[0] + 1;
-            hb[1] = (uint32_t)(stage + 4) | (n << 8) | (*pl.live << 16);
-            if ((threadIdx.x >> 5) == 0) {
-                volatile uint32_t* q = p.heartbeat + blockIdx.x * 64 + 40;
-                for (int s2 = 0; s2 < ST_COUNT; s2++) { q[2 * s2] = pl.wr[s2]; q[2 * s2 + 1] = pl.rd[s2]; }
-            }
-        }
-#endif
         stage = __shfl_sync(0xFFFFFFFFu, stage, 0);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         n = __shfl_sync(0xFFFFFFFFu, n, 0);
@@ -702,6 +678,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_pool_kernel(const PoolPara
             __nanosleep(200);
             continue;
         }
+        sticky = stage;
 
         uint32_t slot = 0;
         const bool has = lane < n;
@@ -722,30 +699,36 @@ __global__ void __launch_bounds__(kThreads, 1) render_pool_kernel(const PoolPara
         if (__any_sync(0xFFFFFFFFu, *pl.abort_flag != 0u)) break;
         __threadfence_block();  // queue entry before slot state
 
-#ifdef RT_POOL_DEBUG
-        if (lane == 0 && p.heartbeat && blockIdx.x < 64)
-            p.heartbeat[blockIdx.x * 64 + (threadIdx.x >> 5) * 2 + 1] = 0x80000000u | (uint32_t)(stage + 1) | (n << 8) | (slot << 16);
-        __syncwarp();
-#endif
         int dest = -1;
-        if (has) {
-            switch (stage) {  // warp-uniform
-                case ST_NODE: dest = stage_node<COUNT>(p, pl, slot, cn); break;
-                case ST_LEAF_TRI: dest = stage_leaf<COUNT, true>(p, pl, slot, cn); break;
-                case ST_LEAF_MIX: dest = stage_leaf<COUNT, false>(p, pl, slot, cn); break;
-                case ST_SHADE: dest = stage_shade<COUNT>(p, pl, slot, cn); break;
-                case ST_SKY: dest = stage_sky<COUNT>(p, pl, slot, cn); break;
-                case ST_CONTINUE: dest = stage_continue(pl, slot, cn); break;
-                default: dest = stage_finish(p, pl, slot, sin_half_fov, cn); break;
-            }
+        constexpr uint32_t B_FIN = 1u << ST_FINISH, B_SHA = 1u << ST_SHADE, B_SKY = 1u << ST_SKY,
+                           B_CON = 1u << ST_CONTINUE, B_TRA = 1u << ST_TRAVERSE;
+        switch (stage) {  // warp-uniform
+            case ST_TRAVERSE:
+                if (has) dest = stage_traverse<COUNT>(p, pl, slot, cn);
+                __syncwarp();
+                publish<B_TRA | B_SHA | B_SKY | B_CON | B_FIN>(pl, dest, slot, lane);
+                break;
+            case ST_SHADE:
+                if (has) dest = stage_shade<COUNT>(p, pl, slot, cn);
+                __syncwarp();
+                publish<B_TRA | B_CON | B_FIN>(pl, dest, slot, lane);
+                break;
+            case ST_SKY:
+                if (has) dest = stage_sky<COUNT>(p, pl, slot, cn);
+                __syncwarp();
+                publish<B_FIN>(pl, dest, slot, lane);
+                break;
+            case ST_CONTINUE:
+                if (has) dest = stage_continue(pl, slot, cn);
+                __syncwarp();
+                publish<B_TRA>(pl, dest, slot, lane);
+                break;
+            default:
+                if (has) dest = stage_finish(p, pl, slot, sin_half_fov, cn);
+                __syncwarp();
+                publish<B_TRA | B_FIN>(pl, dest, slot, lane);
+                break;
         }
-        __syncwarp();
-#ifdef RT_POOL_DEBUG
-        if (lane == 0 && p.heartbeat && blockIdx.x < 64)
-            p.heartbeat[blockIdx.x * 64 + (threadIdx.x >> 5) * 2 + 1] = 0x40000000u | (uint32_t)(stage + 1) | (n << 8);
-        __syncwarp();
-#endif
-        publish(pl, dest, slot, lane);
     }
 
     // ---- counters ----
