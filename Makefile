@@ -43,3 +43,11 @@ oracle/liboracle.so: oracle/shader_oracle.cpp
 
 clean:
 	rm -f $(PKG)/librt_host.so $(PKG)/librt_backend.so $(PKG)/rt_render oracle/liboracle.so
+
+# Host build of the production traversal for the CPU test suite (tests/test_fast_emu.py).
+.PHONY: emu
+emu: tests/emu/libfast_emu.so
+tests/emu/libfast_emu.so: tests/emu/fast_emu.cu $(wildcard $(PKG)/csrc/*.cuh) $(PKG)/csrc/rt_fast_host.hpp include/rt_types.h
+	$(NVCC) -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a --fmad=false -prec-div=true \
+	    -prec-sqrt=true -ftz=false -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math -Iinclude \
+	    -shared -o $@ tests/emu/fast_emu.cu

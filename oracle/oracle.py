@@ -52,6 +52,9 @@ def lib() -> C.CDLL:
         l.oracle_first_hit.restype = C.c_int
         l.oracle_first_hit.argtypes = [C.POINTER(OracleJob), C.c_uint32, C.c_void_p, C.c_void_p,
                                        C.POINTER(OracleCounters), C.c_int]
+        l.oracle_cast_rays.restype = C.c_int
+        l.oracle_cast_rays.argtypes = [C.POINTER(OracleJob), C.c_uint32, C.c_void_p, C.c_void_p,
+                                       C.c_int, C.c_void_p, C.c_void_p]
         l.oracle_trace_pixel.restype = C.c_int
         l.oracle_trace_pixel.argtypes = [C.POINTER(OracleJob), C.c_uint32, C.c_uint32, C.c_uint32,
                                          C.POINTER(C.c_float)]
@@ -118,6 +121,19 @@ class Oracle:
         if st:
             raise RuntimeError("oracle_first_hit: invalid job")
         return slots, t, counters.as_dict()
+
+    def cast_rays(self, origins, dirs, shadow=False):
+        """cast_ray (or the shadow-ray occlusion query) for arbitrary rays [n, 3] float32."""
+        origins = np.ascontiguousarray(origins, dtype=np.float32)
+        dirs = np.ascontiguousarray(dirs, dtype=np.float32)
+        n = origins.shape[0]
+        slots = np.empty(n, dtype=np.uint32)
+        t = np.empty(n, dtype=np.float32)
+        st = lib().oracle_cast_rays(C.byref(self.job), n, origins.ctypes.data, dirs.ctypes.data,
+                                    int(shadow), slots.ctypes.data, t.ctypes.data)
+        if st:
+            raise RuntimeError("oracle_cast_rays: invalid job")
+        return slots, t
 
     def trace_pixel(self, x, y, sample_index):
         rgb = (C.c_float * 3)()

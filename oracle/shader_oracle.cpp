@@ -884,6 +884,30 @@ int oracle_first_hit(const OracleJob* job, uint32_t sample_index, uint32_t* slot
     return 0;
 }
 
+// Arbitrary rays (xyz triples): cast_ray for closest-hit rays (slot/fallback encoding as
+// in oracle_first_hit, distance 0 on a miss) or, with shadow != 0, the occlusion query
+// trace_ray makes (cast_ray_bvh; slot_out = 1 when anything is hit, else 0).
+int oracle_cast_rays(const OracleJob* job, uint32_t n, const float* origins, const float* dirs,
+                     int shadow, uint32_t* slot_out, float* t_out) {
+    if (!job || !job->scene.bvh_node_count || !slot_out) return 1;
+    Ctx ctx{job, Counters{}};
+    std::memset(&ctx.c, 0, sizeof ctx.c);
+    for (uint32_t i = 0; i < n; i++) {
+        Ray ray{ld3(origins + 3 * i), ld3(dirs + 3 * i)};
+        uint32_t slot = RT_MISS_SLOT;
+        if (shadow) {
+            HitInfo h = cast_ray_bvh(ctx, ray, &slot, job->prune != 0);
+            slot_out[i] = h.did_hit ? 1u : 0u;
+            if (t_out) t_out[i] = 0.0f;
+        } else {
+            HitInfo h = cast_ray(ctx, ray, &slot);
+            slot_out[i] = h.did_hit ? slot : RT_MISS_SLOT;
+            if (t_out) t_out[i] = h.did_hit ? h.distance : 0.0f;
+        }
+    }
+    return 0;
+}
+
 // One pixel-sample's radiance (debug / unit tests).
 int oracle_trace_pixel(const OracleJob* job, uint32_t x, uint32_t y, uint32_t sample_index,
                        float rgb[3]) {

@@ -23,6 +23,9 @@
 #include "rt_backend.h"
 #include "rt_device.cuh"
 #include "rt_pool.cuh"
+#include "rt_fast.cuh"
+#include "rt_fast_host.hpp"
+#include "rt_wave.cuh"
 
 using namespace rtd;
 
@@ -361,6 +364,13 @@ struct RtContext {
     float4* d_tri_normals = nullptr;
     float4* d_materials = nullptr;
     SceneView scene{};
+    // fast layout (rt_fast.cuh)
+    float4* d_n2 = nullptr;
+    float4* d_tri = nullptr;
+    float4* d_ana = nullptr;
+    float4* d_pre = nullptr;
+    uint32_t* d_big_len = nullptr;
+    rtf::FastScene fast{};
     uint32_t bvh_depth = 0;
     uint32_t node_count = 0, record_count = 0, material_count = 0;
     bool has_scene = false;
@@ -385,7 +395,15 @@ struct RtContext {
     uint32_t* d_next_pixel = nullptr;
     uint32_t* d_stack_scratch = nullptr;  // only for BVHs deeper than the shared-memory stacks
     int sm_count = 0;
-    bool use_pool = true;
+    enum Kernel { KERNEL_WAVE, KERNEL_FAST, KERNEL_PIXEL, KERNEL_POOL };
+    Kernel kernel = KERNEL_WAVE;
+    // wavefront pipeline state (rt_wave.cuh)
+    rtw::WaveBuffers wave{};
+    void* wave_arena = nullptr;
+    uint32_t wave_slots = 0;       // capacity the arena was allocated for
+    uint32_t wave_max_slots = 2048u * 1024u;
+    uint32_t* wave_live_host = nullptr;  // pinned read-back of WaveCtrl::live, one word per chunk in flight
+    cudaEvent_t wave_events[2] = {nullptr, nullptr};
     bool pool_launched = false;
     bool detailed = false;
     uint64_t launches = 0;
@@ -422,6 +440,13 @@ void free_scene(RtContext* ctx) {
     cudaFree(ctx->d_records);
     cudaFree(ctx->d_tri_normals);
     cudaFree(ctx->d_materials);
+    cudaFree(ctx->d_n2);
+    cudaFree(ctx->d_tri);
+    cudaFree(ctx->d_ana);
+    cudaFree(ctx->d_pre);
+    cudaFree(ctx->d_big_len);
+    ctx->d_n2 = ctx->d_tri = ctx->d_ana = ctx->d_pre = nullptr;
+    ctx->d_big_len = nullptr;
     ctx->d_nodes = ctx->d_records = ctx->d_tri_normals = ctx->d_materials = nullptr;
     ctx->has_scene = false;
 }
@@ -435,11 +460,7 @@ void free_envs(RtContext* ctx) {
     ctx->envs.clear();
 }
 
-inline float bits(uint32_t u) {
-    float f;
-    memcpy(&f, &u, 4);
-    return f;
-}
+using rtf::bits;
 
 // tree_depth (src/bvh.rs:124-134) of the flattened array, iteratively; also validates
 // child / primitive ranges so a malformed upload cannot send a kernel out of bounds.
@@ -484,6 +505,99 @@ bool validate_bvh(const RtSceneDesc& s, uint32_t* depth_out, std::string* why) {
     }
     *depth_out = max_depth;
     return true;
+}
+
+// ---- wavefront pipeline (rt_wave.cuh): buffers and the wave loop ----
+int wave_reserve(RtContext* ctx, uint32_t slots) {
+    if (ctx->wave_arena && ctx->wave_slots >= slots) return RT_OK;
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->wave_arena);
+    ctx->wave_arena = nullptr;
+    ctx->wave_slots = 0;
+    const size_t S = slots;
+    // ray_o, ray_d, sray_d, hit, pT, pL, pP (float4) + pI (uint4) + fb (float2) + occl (u32) + queue (2 x u32) + ctrl
+    const size_t bytes = S * (8 * 16 + 8 + 4 + 8) + 256;
+    RT_CUDA(ctx, cudaMalloc(&ctx->wave_arena, bytes));
+    char* base = (char*)ctx->wave_arena;
+    auto take = [&](size_t n) {
+        char* p = base;
+        base += (n + 255) & ~(size_t)255;
+        return p;
+    };
+    (void)take;
+    char* q = (char*)ctx->wave_arena;
+    rtw::WaveBuffers& b = ctx->wave;
+    b.ray_o = (float4*)q;  q += S * 16;
+    b.ray_d = (float4*)q;  q += S * 16;
+    b.sray_d = (float4*)q; q += S * 16;
+    b.hit = (float4*)q;    q += S * 16;
+    b.pT = (float4*)q;     q += S * 16;
+    b.pL = (float4*)q;     q += S * 16;
+    b.pP = (float4*)q;     q += S * 16;
+    b.pI = (uint4*)q;      q += S * 16;
+    b.fb = (float2*)q;     q += S * 8;
+    b.queue = (uint32_t*)q; q += S * 8;
+    b.occl = (uint32_t*)q; q += S * 4;
+    q = (char*)(((uintptr_t)q + 15) & ~(uintptr_t)15);
+    b.ctrl = (rtw::WaveCtrl*)q;
+    ctx->wave_slots = slots;
+    return RT_OK;
+}
+
+// Runs waves until every slot has retired. The host only paces the launches: it reads the
+// live-slot count one chunk behind the launches, so the stream never runs dry.
+int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, uint32_t sample_count,
+                uint32_t max_bounces) {
+    rtw::WaveParams p;
+    memset(&p, 0, sizeof p);
+    p.scene = ctx->fast;
+    p.env.texture = e.texture;
+    p.env.alias = e.d_alias;
+    p.env.width = e.width;
+    p.env.height = e.height;
+    p.camera = ctx->camera;
+    p.accum = ctx->d_accum;
+    p.counters = ctx->d_counters;
+    p.width = ctx->width;
+    p.height = ctx->height;
+    p.tiles_x = (ctx->width + 7u) / 8u;
+    p.pixel_ids = p.tiles_x * ((ctx->height + 7u) / 8u) * 64u;
+    p.slots = p.pixel_ids < ctx->wave_max_slots ? p.pixel_ids : ctx->wave_max_slots;
+    p.sample_begin = sample_begin;
+    p.sample_count = sample_count;
+    p.max_bounces = max_bounces;
+    int st = wave_reserve(ctx, p.slots);
+    if (st != RT_OK) return st;
+    p.b = ctx->wave;
+
+    const unsigned logic_blocks = (p.slots + rtw::kLogicThreads - 1) / rtw::kLogicThreads;
+    unsigned trace_blocks = (unsigned)ctx->sm_count * RT_WAVE_TRACE_MIN_BLOCKS;
+    const unsigned trace_needed = (2u * p.slots + rtw::kTraceThreads - 1) / rtw::kTraceThreads;
+    if (trace_blocks > trace_needed) trace_blocks = trace_needed;
+    rtw::wave_init_kernel<<<(p.slots + 255) / 256, 256, 0, ctx->stream>>>(p);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+
+    const uint32_t chunk = 24;
+    uint32_t wave = 0;
+    for (uint32_t k = 0;; k++) {
+        for (uint32_t i = 0; i < chunk; i++, wave++) {
+            p.wave = wave;
+            rtw::wave_logic_kernel<<<logic_blocks, rtw::kLogicThreads, 0, ctx->stream>>>(p);
+            rtw::wave_trace_kernel<<<trace_blocks, rtw::kTraceThreads, 0, ctx->stream>>>(p);
+            ctx->launches += 2;
+        }
+        RT_CUDA(ctx, cudaGetLastError());
+        RT_CUDA(ctx, cudaMemcpyAsync(&ctx->wave_live_host[k & 1u], &p.b.ctrl[(wave - 1u) & 1u].live, sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+        RT_CUDA(ctx, cudaEventRecord(ctx->wave_events[k & 1u], ctx->stream));
+        if (k > 0) {
+            RT_CUDA(ctx, cudaEventSynchronize(ctx->wave_events[(k - 1u) & 1u]));
+            if (ctx->wave_live_host[(k - 1u) & 1u] == 0u) break;  // the chunk after it only ran empty waves
+        }
+        if (wave > 0x7FFFFF00u) return fail(ctx, RT_ERR_STATE, "wave loop did not terminate");
+    }
+    return RT_OK;
 }
 
 template <bool COUNT>
@@ -584,7 +698,21 @@ int rt_create(int device, RtContext** out) {
         (e = cudaFuncSetAttribute(rtp::render_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)rtp::pool_smem_bytes())) != cudaSuccess)
         return bail("cudaFuncSetAttribute(shared memory)", e);
-    if (const char* k = getenv("RT_KERNEL")) ctx->use_pool = strcmp(k, "pixel") != 0;
+    if (const char* k = getenv("RT_KERNEL")) {
+        // Development switch: the reference-order kernels are kept for the detailed work counters.
+        if (!strcmp(k, "pixel")) ctx->kernel = RtContext::KERNEL_PIXEL;
+        else if (!strcmp(k, "fast")) ctx->kernel = RtContext::KERNEL_FAST;
+        else if (!strcmp(k, "pool")) ctx->kernel = RtContext::KERNEL_POOL;
+    }
+    if (const char* k = getenv("RT_WAVE_SLOTS")) {
+        long v = atol(k);
+        if (v >= 1024 && v <= (1l << 24)) ctx->wave_max_slots = (uint32_t)v;
+    }
+    if ((e = cudaHostAlloc(&ctx->wave_live_host, 2 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess)
+        return bail("cudaHostAlloc", e);
+    for (int i = 0; i < 2; i++)
+        if ((e = cudaEventCreateWithFlags(&ctx->wave_events[i], cudaEventDisableTiming)) != cudaSuccess)
+            return bail("cudaEventCreate", e);
     *out = ctx;
     return RT_OK;
 }
@@ -599,6 +727,10 @@ void rt_destroy(RtContext* ctx) {
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_next_pixel);
     cudaFree(ctx->d_stack_scratch);
+    cudaFree(ctx->wave_arena);
+    if (ctx->wave_live_host) cudaFreeHost(ctx->wave_live_host);
+    for (int i = 0; i < 2; i++)
+        if (ctx->wave_events[i]) cudaEventDestroy(ctx->wave_events[i]);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -723,6 +855,32 @@ int rt_upload_scene(RtContext* ctx, const RtSceneDesc* s) {
     RT_CUDA(ctx, cudaMemcpyAsync(d_raw_materials, s->materials,
                                  (size_t)s->material_count * sizeof(RtMaterial),
                                  cudaMemcpyHostToDevice, ctx->stream));
+    {
+        if (slots >= rtf::kLeafSlotMask)
+            return fail(ctx, RT_ERR_INVALID_ARGUMENT, "too many primitives (%u) for the 26-bit leaf slot field", slots);
+        rtf::FastLayout fl;
+        rtf::build_fast_layout(*s, fl);
+        RT_CUDA(ctx, cudaMalloc(&ctx->d_n2, fl.n2.size() * sizeof(float4)));
+        RT_CUDA(ctx, cudaMalloc(&ctx->d_tri, (fl.tri.size() + 1) * sizeof(float4)));
+        RT_CUDA(ctx, cudaMalloc(&ctx->d_ana, fl.ana.size() * sizeof(float4)));
+        RT_CUDA(ctx, cudaMalloc(&ctx->d_pre, fl.pre.size() * sizeof(float4)));
+        RT_CUDA(ctx, cudaMemcpy(ctx->d_n2, fl.n2.data(), fl.n2.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        if (!fl.tri.empty())
+            RT_CUDA(ctx, cudaMemcpy(ctx->d_tri, fl.tri.data(), fl.tri.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        RT_CUDA(ctx, cudaMemcpy(ctx->d_ana, fl.ana.data(), fl.ana.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        RT_CUDA(ctx, cudaMemcpy(ctx->d_pre, fl.pre.data(), fl.pre.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        if (!fl.big_len.empty()) {
+            RT_CUDA(ctx, cudaMalloc(&ctx->d_big_len, fl.big_len.size() * sizeof(uint32_t)));
+            RT_CUDA(ctx, cudaMemcpy(ctx->d_big_len, fl.big_len.data(), fl.big_len.size() * sizeof(uint32_t),
+                                    cudaMemcpyHostToDevice));
+        }
+        ctx->fast = fl.view;
+        ctx->fast.n2 = ctx->d_n2;
+        ctx->fast.tri = ctx->d_tri;
+        ctx->fast.ana = ctx->d_ana;
+        ctx->fast.pre = ctx->d_pre;
+        ctx->fast.big_len = ctx->d_big_len;
+    }
     bake_materials_kernel<<<(s->material_count + 127) / 128, 128, 0, ctx->stream>>>(
         d_raw_materials, ctx->d_materials, s->material_count);
     ctx->launches++;
@@ -734,9 +892,12 @@ int rt_upload_scene(RtContext* ctx, const RtSceneDesc* s) {
     ctx->scene.records = ctx->d_records;
     ctx->scene.tri_normals = ctx->d_tri_normals;
     ctx->scene.materials = ctx->d_materials;
+    ctx->fast.tri_normals = ctx->d_tri_normals;
+    ctx->fast.materials = ctx->d_materials;
     ctx->scene.slot_count = slots;
     ctx->scene.sphere_count = s->sphere_count;
     ctx->scene.plane_count = s->plane_count;
+    ctx->scene.prune = rtf::scene_has_loose_plane(*s) ? 0u : 1u;
     ctx->bvh_depth = depth;
     ctx->node_count = s->bvh_node_count;
     ctx->record_count = (uint32_t)rec_count;
@@ -864,7 +1025,30 @@ int rt_render(RtContext* ctx, uint32_t sample_begin, uint32_t sample_count, uint
         zero_bounce_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(
             ctx->d_accum, count, ctx->d_counters, sample_count);
         e2 = cudaGetLastError();
-    } else if (ctx->use_pool) {
+    } else if (ctx->kernel == RtContext::KERNEL_WAVE && !ctx->detailed) {
+        return wave_render(ctx, e, sample_begin, sample_count, max_bounces);
+    } else if (ctx->kernel == RtContext::KERNEL_FAST && !ctx->detailed) {
+        rtf::FastParams p;
+        p.scene = ctx->fast;
+        p.env.texture = e.texture;
+        p.env.alias = e.d_alias;
+        p.env.width = e.width;
+        p.env.height = e.height;
+        p.camera = ctx->camera;
+        p.accum = ctx->d_accum;
+        p.counters = ctx->d_counters;
+        p.slot_out = nullptr;
+        p.t_out = nullptr;
+        p.width = ctx->width;
+        p.height = ctx->height;
+        p.sample_begin = sample_begin;
+        p.sample_count = sample_count;
+        p.max_bounces = max_bounces;
+        p.sphere_count = ctx->scene.sphere_count;
+        dim3 grid((p.width + rtf::kFastTileW - 1) / rtf::kFastTileW, (p.height + rtf::kFastTileH - 1) / rtf::kFastTileH);
+        rtf::render_fast_kernel<<<grid, rtf::kFastThreads, 0, ctx->stream>>>(p);
+        e2 = cudaGetLastError();
+    } else if (ctx->kernel == RtContext::KERNEL_POOL) {
         rtp::PoolParams p;
         p.scene = ctx->scene;
         p.env.texture = e.texture;
@@ -945,8 +1129,26 @@ int rt_first_hit(RtContext* ctx, uint32_t sample_index, uint32_t* slot_out, floa
     p.width = ctx->width;
     p.height = ctx->height;
     p.sample = sample_index;
-    e = ctx->detailed ? launch_first_hit<true>(p, ctx->bvh_depth, ctx->stream)
-                      : launch_first_hit<false>(p, ctx->bvh_depth, ctx->stream);
+    if ((ctx->kernel == RtContext::KERNEL_FAST || ctx->kernel == RtContext::KERNEL_WAVE) && !ctx->detailed) {
+        rtf::FastParams fp;
+        memset(&fp, 0, sizeof fp);
+        fp.scene = ctx->fast;
+        fp.camera = ctx->camera;
+        fp.counters = ctx->d_counters;
+        fp.slot_out = d_slot;
+        fp.t_out = d_t;
+        fp.width = ctx->width;
+        fp.height = ctx->height;
+        fp.sample_begin = sample_index;
+        fp.sphere_count = ctx->scene.sphere_count;
+        dim3 grid((fp.width + rtf::kFastTileW - 1) / rtf::kFastTileW,
+                  (fp.height + rtf::kFastTileH - 1) / rtf::kFastTileH);
+        rtf::first_hit_fast_kernel<<<grid, rtf::kFastThreads, 0, ctx->stream>>>(fp);
+        e = cudaGetLastError();
+    } else {
+        e = ctx->detailed ? launch_first_hit<true>(p, ctx->bvh_depth, ctx->stream)
+                          : launch_first_hit<false>(p, ctx->bvh_depth, ctx->stream);
+    }
     ctx->launches++;
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(slot_out, d_slot, count * 4, cudaMemcpyDeviceToHost, ctx->stream);

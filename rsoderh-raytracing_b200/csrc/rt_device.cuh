@@ -10,10 +10,40 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace rtd {
 
+// RT_HOST_EMU (tests only) also compiles the ray-casting routines for the host, so the
+// CPU test suite can exercise the kernels' traversal logic without a GPU (tests/emu/).
+#ifdef RT_HOST_EMU
+#define RT_DEV __host__ __device__ __forceinline__
+#define RT_COLD __host__ __device__ __noinline__
+#else
 #define RT_DEV __device__ __forceinline__
+#define RT_COLD __device__ __noinline__
+#endif
+#define RT_DEVONLY __device__ __forceinline__
+
+RT_DEV uint32_t f_as_u(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+#endif
+}
+RT_DEV int f_as_i(float f) { return (int)f_as_u(f); }
+RT_DEV float u_as_f(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
 
 // ---------------------------------------------------------------------------------
 // Small vector helpers (WGSL evaluation order).
@@ -158,6 +188,7 @@ struct SceneView {
     uint32_t slot_count;      // leaf slots; fallback spheres start here
     uint32_t sphere_count;
     uint32_t plane_count;
+    uint32_t prune;           // 0 when a plane may stick out of its leaf box (rt_fast_host.hpp)
 };
 
 struct EnvView {
@@ -177,7 +208,13 @@ struct Counts {
     uint32_t nodes, tris, spheres, planes, hits, tri_hits, shaded, env_lookups, fallback;
 };
 
-RT_DEV float4 ld4(const float4* p) { return __ldg(p); }
+RT_DEV float4 ld4(const float4* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 
 // ---------------------------------------------------------------------------------
 // Primitive tests. Each returns the candidate distance or leaves `hit` false; the
@@ -252,7 +289,7 @@ template <bool COUNT>
 RT_DEV void test_record(const SceneView& sc, uint32_t rec, V3 o, V3 d, Hit& best, Counts& cn) {
     const float4* p = sc.records + 4u * (size_t)rec;
     float4 r0 = ld4(p), r1 = ld4(p + 1);
-    int type = __float_as_int(r0.w);
+    int type = f_as_i(r0.w);
     float t = 0.0f, u = 0.0f, v = 0.0f;
     bool hit;
     if (type == 2) {
@@ -348,8 +385,8 @@ RT_TRACE_QUAL void trace(const SceneView& sc, V3 o, V3 d, bool any_hit, bool wit
             }
             uint32_t next = RT_NONE;  // where to go if this node yields nothing to descend into
             if (!(t0 > t1)) {
-                const uint32_t idx = __float_as_uint(n0.w);
-                const uint32_t meta = __float_as_uint(n1.w);
+                const uint32_t idx = f_as_u(n0.w);
+                const uint32_t meta = f_as_u(n1.w);
                 const uint32_t len = meta & 0x1FFFFFFFu;
                 if (len > 0u) {
                     leaf_begin = idx;
@@ -378,7 +415,7 @@ RT_TRACE_QUAL void trace(const SceneView& sc, V3 o, V3 d, bool any_hit, bool wit
             if (any_hit && best.rec != RT_NONE) return;
         }
         leaf_begin = leaf_end = 0u;
-        limit = fminf(RT_INFINITY, best.t * 1.001f);
+        if (sc.prune) limit = fminf(RT_INFINITY, best.t * 1.001f);
     }
 }
 
@@ -387,7 +424,7 @@ RT_DEV void reconstruct_hit(const SceneView& sc, V3 o, V3 d, const Hit& h, V3& p
                             uint32_t& material) {
     const float4* p = sc.records + 4u * (size_t)h.rec;
     float4 r0 = ld4(p), r1 = ld4(p + 1);
-    int type = __float_as_int(r0.w);
+    int type = f_as_i(r0.w);
     point = o + d * h.t;
     if (type == 2) {
         // shader.wgsl:446-457
@@ -396,7 +433,7 @@ RT_DEV void reconstruct_hit(const SceneView& sc, V3 o, V3 d, const Hit& h, V3& p
         V3 n = normalize(((1.0f - h.u - h.v) * n0 + h.u * n1) + h.v * n2);
         if (dot(n, d) > 0.0f) n = n * -1.0f;
         normal = n;
-        material = __float_as_uint(r1.w);
+        material = f_as_u(r1.w);
     } else if (type == 0) {
         // shader.wgsl:335-351; length_squared(pos - origin) - r^2 equals `c` bit for bit.
         V3 pos = xyz(r0);
@@ -404,13 +441,13 @@ RT_DEV void reconstruct_hit(const SceneView& sc, V3 o, V3 d, const Hit& h, V3& p
         V3 l = pos - o;
         if (dot(l, l) - r1.y < 1.0e-6f) n = n * -1.0f;
         normal = n;
-        material = __float_as_uint(r1.z);
+        material = f_as_u(r1.z);
     } else {
         // shader.wgsl:393-397 (sic: the flip tests the ray origin against the world origin)
         V3 n = xyz(r1);
         if (dot(o, n) < 0.0f) n = n * -1.0f;
         normal = n;
-        material = __float_as_uint(r1.w);
+        material = f_as_u(r1.w);
     }
 }
 
@@ -432,7 +469,7 @@ RT_DEV float pixel_solid_angle(float v, const EnvView& env) {
 
 // textureSampleLevel(.., uv, 0) under the reference sampler (clamp-to-edge, linear):
 // four point fetches through the texture unit and an f32 bilinear blend.
-RT_DEV V3 env_bilinear(const EnvView& env, float u, float v) {
+RT_DEVONLY V3 env_bilinear(const EnvView& env, float u, float v) {
     float fx = u * (float)env.width - 0.5f;
     float fy = v * (float)env.height - 0.5f;
     float x0f = floorf(fx), y0f = floorf(fy);

@@ -164,7 +164,7 @@ RT_DEV int stage_traverse(const PoolParams& p, Pool& pl, uint32_t slot, Counts& 
     best.rec = pl.getu(F_BR, slot);
     best.u = pl.getf(F_BU, slot);
     best.v = pl.getf(F_BV, slot);
-    float limit = fminf(RT_INFINITY, best.t * 1.001f);
+    float limit = p.scene.prune ? fminf(RT_INFINITY, best.t * 1.001f) : RT_INFINITY;
     uint32_t budget = kNodeBudget;
     uint32_t leaf_begin = 0u, leaf_end = 0u;
     bool leaf_mixed = false;
@@ -261,7 +261,7 @@ RT_DEV int stage_traverse(const PoolParams& p, Pool& pl, uint32_t slot, Counts& 
             return (flags & FLAG_ENDS) ? ST_FINISH : ST_CONTINUE;
         }
         leaf_begin = leaf_end = 0u;
-        limit = fminf(RT_INFINITY, best.t * 1.001f);
+        if (p.scene.prune) limit = fminf(RT_INFINITY, best.t * 1.001f);
     }
 
     if (cur != RT_NONE) {
