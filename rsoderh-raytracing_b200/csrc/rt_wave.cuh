@@ -1,20 +1,23 @@
 // rt_wave.cuh — the wavefront render pipeline: the path loop of shader.wgsl:1213-1303 cut at
-// its ray casts and run as two small kernels per "wave".
+// its ray casts and run as four small, dense kernels per "wave".
 //
 // Why: as one kernel (rt_fast.cuh's render_fast_kernel) the loop body is ~60 KB of SASS — far
 // beyond the 32 KB instruction cache level — and a warp's lanes sit in different parts of
 // it: ncu showed 40 % issue utilisation with "no instruction" as the top stall and 8 to 10
-// of 32 lanes active. Here
-//   * `wave_logic_kernel` (one thread per path slot) consumes last wave's results — settles
-//     the shadow ray, adds sky light or shades the hit, accumulates finished samples and
-//     starts the pixel's next one — then runs the analytic pre-pass for the rays it emits,
-//     all lanes together, and queues them;
-//   * `wave_trace_kernel` is the triangle walk alone (a few KB of code): persistent warps
-//     whose lanes each pull the next ray from the queue the moment their own is finished,
-//     so closest-hit and shadow rays of the whole frame share the lanes.
-// The next bounce's ray and the shadow ray of the same hit do not depend on each other and
-// travel in the same wave. Path state lives in global memory, sized so that one wave's
-// working set (~170 B per slot) stays inside the 126 MB L2.
+// of 32 lanes active. Here every kernel does ONE thing for a compacted list of path slots,
+// so all 32 lanes of a warp run the same code:
+//   wave_shade_kernel    slots whose ray hit -> settle last shadow ray, shade (emission,
+//                        next-event set-up, BSDF sample), emit the bounce ray + shadow ray
+//   wave_finish_kernel   slots whose path is over / ray escaped / are new -> settle, sky light,
+//                        accumulate the sample, start the pixel's next one (camera ray)
+//   wave_prepass_kernel  ray queue -> the analytic pre-pass (rt_fast.cuh) of every emitted ray
+//   wave_walk_kernel     ray queue -> the triangle walk alone (a few KB of code): persistent
+//                        warps whose lanes pull the next ray the moment their own is finished
+// shade and finish find their slots by sweeping a one-byte stage array in slot order and
+// compacting inside the warp (ballot + a small shared-memory list), so a warp's 32 lanes work
+// on 32 NEARBY slots: full lanes and coalesced state traffic, no global lists.
+// The bounce ray and the shadow ray of one hit do not depend on each other and travel in
+// the same wave. Path state lives in global memory (~170 B per slot).
 //
 // A slot owns one pixel for all of that pixel's samples and traces them in sample order,
 // then moves to its next pixel (slot + k * slot_count in an 8x8-tile-major numbering), so
@@ -28,35 +31,57 @@ namespace rtw {
 using namespace rtd;
 using namespace rtf;
 
-constexpr uint32_t kShadowBit = 0x80000000u;  // queue entry: the slot's shadow ray
-constexpr int kLogicThreads = 128;
-constexpr int kTraceThreads = 256;
+constexpr uint32_t kShadowBit = 0x80000000u;  // ray queue entry: the slot's shadow ray
+constexpr uint32_t kDeadEntry = 0xFFFFFFFFu;  // ray queue entry settled by the pre-pass
+constexpr int kShadeThreads = 128;
+constexpr int kFinishThreads = 128;
+constexpr int kPrepassThreads = 256;
+constexpr int kWalkThreads = 256;
 
-enum SlotState : uint32_t { SLOT_RETIRED = 0, SLOT_NEW = 1, SLOT_TRACED = 2, SLOT_ENDING = 3 };
+// pI.w of a slot
+enum SlotState : uint32_t {
+    SLOT_RETIRED = 0,
+    SLOT_NEW = 1,     // needs its first camera ray
+    SLOT_TRACED = 2,  // a closest-hit ray is in flight / has come back
+    SLOT_ENDING = 3,  // the path is over but its last shadow ray is still in flight
+    SLOT_DONE = 4     // the path is over, nothing in flight
+};
 constexpr uint32_t kFlagShadow = 1u;  // a shadow ray was cast for the last shaded hit
 
-// Control block, one per wave parity: the logic kernel of wave w fills ctrl[w & 1] and
-// clears ctrl[(w + 1) & 1] for the next wave.
+// stage[slot]
+enum SlotStage : uint8_t {
+    STAGE_IDLE = 0,         // retired
+    STAGE_SHADE = 1,        // its closest-hit ray hit something
+    STAGE_FINISH = 2,       // its ray escaped, its path ended, or it is new
+    STAGE_FLIGHT = 3,       // a closest-hit ray is in flight
+    STAGE_FINISH_NEXT = 4   // path over, last shadow ray in flight: finish in the next wave
+};
+
+// The ray queue is double-buffered by wave parity P = wave & 1: ray_n[P], ray_head[P] are
+// filled by shade(w) + finish(w) and read by prepass(w) + walk(w); shade(w) clears the other.
 struct WaveCtrl {
-    uint32_t queued;  // rays appended to the queue
-    uint32_t head;    // rays handed out by the trace kernel
-    uint32_t live;    // slots still working after this wave's logic pass
-    uint32_t pad;
+    uint32_t ray_n[2];
+    uint32_t ray_head[2];
+    uint32_t live;  // slots not yet retired
+    uint32_t pad[3];
 };
 
 struct WaveBuffers {
+    // Structure of arrays (measured faster than one 128-byte record per slot: the pre-pass and
+    // the walk touch only the ray vectors).
     float4* ray_o;    // [S] origin of the slot's rays, .w = closest analytic distance from the pre-pass
     float4* ray_d;    // [S] direction of the closest-hit ray, .w = bits rec of that analytic hit
     float4* sray_d;   // [S] direction of the shadow ray
     float2* fb;       // [S] brute-force fallback winner of the closest-hit ray (t, bits index)
-    float4* hit;      // [S] (t, bits rec, u, v) written by the trace kernel
+    float4* hit;      // [S] (t, bits rec, u, v) written by the walk kernel
     uint32_t* occl;   // [S] 1 when the shadow ray is blocked
     float4* pT;       // [S] throughput, last_pdf
     float4* pL;       // [S] radiance of the current sample, bits rng
     float4* pP;       // [S] pending next-event light, bits flags
     uint4* pI;        // [S] pixel id, sample, bounce, state
-    uint32_t* queue;  // [2S]
-    WaveCtrl* ctrl;   // [2]
+    uint8_t* stage;   // [S] what the slot needs next (SlotStage)
+    uint32_t* rayq;   // [2][2S]
+    WaveCtrl* ctrl;
 };
 
 struct WaveParams {
@@ -68,7 +93,9 @@ struct WaveParams {
     unsigned long long* counters;
     uint32_t width, height;
     uint32_t tiles_x, pixel_ids;  // 8x8-tile-major pixel numbering (ids of partial tiles included)
-    uint32_t slots;
+    uint32_t slots;        // slots of this group (buffers are indexed 0 .. slots-1)
+    uint32_t slot_base;    // first pixel id of this group's slot 0
+    uint32_t slot_stride;  // pixel ids between a slot's consecutive pixels = slots of all groups
     uint32_t sample_begin, sample_count;
     uint32_t max_bounces;
     uint32_t wave;
@@ -85,210 +112,311 @@ RT_DEVONLY bool pixel_of_id(const WaveParams& p, uint32_t id, uint32_t& px, uint
 RT_DEVONLY uint32_t next_pixel_id(const WaveParams& p, uint32_t id, uint32_t& px, uint32_t& py) {
     while (id < p.pixel_ids) {
         if (pixel_of_id(p, id, px, py)) return id;
-        id += p.slots;
+        id += p.slot_stride;
     }
     return kNone;
 }
 
-__global__ void wave_init_kernel(const WaveParams p) {
-    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot < p.slots) p.b.pI[slot] = make_uint4(slot, p.sample_begin, 0u, SLOT_NEW);
-    if (slot < 2) {
-        p.b.ctrl[slot].queued = 0u;
-        p.b.ctrl[slot].head = 0u;
-        p.b.ctrl[slot].live = 0u;
-    }
-}
-
-// Appends one entry per requesting lane with a single atomic per warp.
-RT_DEVONLY void queue_push(const WaveParams& p, WaveCtrl* ctrl, bool want, uint32_t entry) {
+// Appends one entry per requesting lane with a single atomic per warp. Every lane of the
+// warp must call it.
+RT_DEVONLY void list_push(uint32_t* list, uint32_t* count, bool want, uint32_t entry) {
     const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
     if (!m) return;
     const uint32_t lane = threadIdx.x & 31u;
     const int leader = __ffs(m) - 1;
     uint32_t base = 0;
-    if ((int)lane == leader) base = atomicAdd(&ctrl->queued, (uint32_t)__popc(m));
+    if ((int)lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
     base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    if (want) p.b.queue[base + __popc(m & ((1u << lane) - 1u))] = entry;
+    if (want) list[base + __popc(m & ((1u << lane) - 1u))] = entry;
 }
 
-#ifndef RT_WAVE_LOGIC_MIN_BLOCKS
-#define RT_WAVE_LOGIC_MIN_BLOCKS 4
+// Path state streams through memory once per wave: load / store it "cache streaming" (evict
+// first) so that it does not push the environment map, alias table and scene out of L2.
+#ifndef RT_WAVE_STREAM
+#define RT_WAVE_STREAM 0
+#endif
+template <typename T>
+RT_DEVONLY T lds(const T* ptr) {
+#if RT_WAVE_STREAM
+    return __ldcs(ptr);
+#else
+    return *ptr;
+#endif
+}
+template <typename T>
+RT_DEVONLY void sts(T* ptr, T v) {
+#if RT_WAVE_STREAM
+    __stcs(ptr, v);
+#else
+    *ptr = v;
+#endif
+}
+
+__global__ void wave_init_kernel(const WaveParams p) {
+    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < p.slots) {
+        sts(&p.b.pI[slot], make_uint4(p.slot_base + slot, p.sample_begin, 0u, SLOT_NEW));
+        p.b.stage[slot] = STAGE_FINISH;  // every slot starts its first path in wave 0's finish pass
+    }
+    if (slot == 0) {
+        WaveCtrl c;
+        memset(&c, 0, sizeof c);
+        c.live = p.slots;
+        *p.b.ctrl = c;
+    }
+}
+
+struct PathRegs {
+    V3 T, L, pending;
+    float last_pdf;
+    uint32_t rng, flags;
+};
+
+RT_DEVONLY void load_path(const WaveParams& p, uint32_t slot, PathRegs& s) {
+    const float4 t4 = lds(&p.b.pT[slot]), l4 = lds(&p.b.pL[slot]), p4 = lds(&p.b.pP[slot]);
+    s.T = xyz(t4);
+    s.last_pdf = t4.w;
+    s.L = xyz(l4);
+    s.rng = f_as_u(l4.w);
+    s.pending = xyz(p4);
+    s.flags = f_as_u(p4.w);
+}
+
+RT_DEVONLY void store_path(const WaveParams& p, uint32_t slot, const PathRegs& s) {
+    sts(&p.b.pT[slot], make_float4(s.T.x, s.T.y, s.T.z, s.last_pdf));
+    sts(&p.b.pL[slot], make_float4(s.L.x, s.L.y, s.L.z, u_as_f(s.rng)));
+    sts(&p.b.pP[slot], make_float4(s.pending.x, s.pending.y, s.pending.z, u_as_f(s.flags)));
+}
+
+// shader.wgsl:1249-1264: the last next-event sample counts iff nothing blocked its ray.
+RT_DEVONLY void settle_shadow(const WaveParams& p, uint32_t slot, PathRegs& s) {
+    if ((s.flags & kFlagShadow) && lds(&p.b.occl[slot]) == 0u) s.L = s.L + s.pending;
+    s.flags = 0u;
+}
+
+#ifndef RT_WAVE_SHADE_MIN_BLOCKS
+#define RT_WAVE_SHADE_MIN_BLOCKS 8
 #endif
 
-__global__ void __launch_bounds__(kLogicThreads, RT_WAVE_LOGIC_MIN_BLOCKS) wave_logic_kernel(const WaveParams p) {
-    __shared__ float4 spre[kPreMaxFloat4];
-    stage_pre(p.scene, spre);
-
-    WaveCtrl* ctrl = p.b.ctrl + (p.wave & 1u);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        WaveCtrl* other = p.b.ctrl + ((p.wave + 1u) & 1u);
-        other->queued = 0u;
-        other->head = 0u;
-        other->live = 0u;
+// Sweeps `stage` in slot order; `body(slot, on)` runs with up to 32 compacted slots per
+// warp call (on == false for lanes without one). Leftovers are carried to the next chunk so
+// the lanes stay full; every lane of the warp reaches every body call.
+template <int THREADS, typename Body>
+RT_DEVONLY void sweep_stage(const WaveParams& p, uint8_t want, uint8_t convert_from, uint8_t convert_to,
+                            Body&& body) {
+    __shared__ uint32_t lists[THREADS / 32][64];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t* list = lists[warp];
+    const uint32_t warps = gridDim.x * (THREADS / 32);
+    const uint32_t chunks = (p.slots + 31u) / 32u;
+    uint32_t n = 0;
+    for (uint32_t chunk = blockIdx.x * (THREADS / 32) + warp; chunk < chunks; chunk += warps) {
+        const uint32_t slot = chunk * 32u + lane;
+        uint8_t st = slot < p.slots ? p.b.stage[slot] : (uint8_t)STAGE_IDLE;
+        if (convert_from && st == convert_from) p.b.stage[slot] = convert_to;
+        const bool need = st == want;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, need);
+        if (need) list[n + __popc(m & ((1u << lane) - 1u))] = slot;
+        n += __popc(m);
+        __syncwarp();
+        if (n >= 32u) {
+            body(list[lane], true);
+            n -= 32u;
+            const uint32_t carry = lane < n ? list[32u + lane] : 0u;
+            __syncwarp();
+            if (lane < n) list[lane] = carry;
+            __syncwarp();
+        }
     }
+    if (n > 0u) body(lane < n ? list[lane] : 0u, lane < n);
+}
 
-    const uint32_t slot = blockIdx.x * kLogicThreads + threadIdx.x;
-    uint4 I = slot < p.slots ? p.b.pI[slot] : make_uint4(0u, 0u, 0u, SLOT_RETIRED);
-    uint32_t state = I.w;
-    uint32_t n_paths = 0, n_rays = 0, n_shadow = 0;
-    bool emit_closest = false, emit_shadow = false, shadow_blocked = false;
-    V3 o = v3s(0.f), d = v3s(0.f), sdir = v3s(0.f);
-
-    if (state != SLOT_RETIRED) {
-        const uint32_t sample_end = p.sample_begin + p.sample_count;
-        V3 T = v3s(1.f), L = v3s(0.f), pending = v3s(0.f);
-        float last_pdf = 1.0f;
-        uint32_t rng = 0u, flags = 0u, bounce = I.z;
-        bool finish = false, fresh = state == SLOT_NEW;
-        if (!fresh) {
-            const float4 t4 = p.b.pT[slot], l4 = p.b.pL[slot], p4 = p.b.pP[slot];
-            T = xyz(t4);
-            last_pdf = t4.w;
-            L = xyz(l4);
-            rng = f_as_u(l4.w);
-            pending = xyz(p4);
-            flags = f_as_u(p4.w);
-            // shader.wgsl:1249-1264: the next-event sample counts iff nothing blocks it.
-            if ((flags & kFlagShadow) && p.b.occl[slot] == 0u) L = L + pending;
-            flags = 0u;
-            if (state == SLOT_ENDING) {
-                finish = true;
+// Slots whose ray hit something: shade, emit the next rays.
+__global__ void __launch_bounds__(kShadeThreads, RT_WAVE_SHADE_MIN_BLOCKS) wave_shade_kernel(const WaveParams p) {
+    const uint32_t P = p.wave & 1u, Q = P ^ 1u;
+    WaveCtrl* c = p.b.ctrl;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        c->ray_n[Q] = 0u;  // next wave's ray queue
+        c->ray_head[Q] = 0u;
+    }
+    uint32_t* rayq = p.b.rayq + (size_t)P * 2u * p.slots;
+    uint32_t n_rays = 0, n_shadow = 0;
+    sweep_stage<kShadeThreads>(p, STAGE_SHADE, 0, 0, [&](uint32_t slot, bool on) {
+        bool emit_closest = false, emit_shadow = false;
+        if (on) {
+            PathRegs s;
+            load_path(p, slot, s);
+            settle_shadow(p, slot, s);
+            uint4 I = lds(&p.b.pI[slot]);
+            const float4 o4 = lds(&p.b.ray_o[slot]), d4 = lds(&p.b.ray_d[slot]), h4 = lds(&p.b.hit[slot]);
+            FHit hit;
+            hit.t = h4.x;
+            hit.rec = f_as_u(h4.y);
+            hit.u = h4.z;
+            hit.v = h4.w;
+            ShadeOut so;
+            shade_hit(p.scene, p.env, xyz(o4), xyz(d4), hit, s.rng, s.T, s.L, so);
+            I.z++;
+            const bool done = so.done || I.z >= p.max_bounces;
+            s.last_pdf = so.next_pdf;
+            s.pending = so.pending;
+            if (so.want_shadow) {
+                emit_shadow = true;
+                s.flags = kFlagShadow;
+                sts(&p.b.sray_d[slot], make_float4(so.shadow_dir.x, so.shadow_dir.y, so.shadow_dir.z, 0.0f));
+                sts(&p.b.occl[slot], 0u);
+                n_shadow++;
+            }
+            // Both rays start at the hit point (no offset: shader.wgsl:1249, 1295).
+            sts(&p.b.ray_o[slot], make_float4(so.point.x, so.point.y, so.point.z, RT_INFINITY));
+            if (done) {
+                // With a shadow ray in flight the sample is finished one wave later.
+                I.w = emit_shadow ? SLOT_ENDING : SLOT_DONE;
+                p.b.stage[slot] = emit_shadow ? STAGE_FINISH_NEXT : STAGE_FINISH;
             } else {
-                const float4 o4 = p.b.ray_o[slot], d4 = p.b.ray_d[slot], h4 = p.b.hit[slot];
-                o = xyz(o4);
-                d = xyz(d4);
-                FHit hit;
-                hit.t = h4.x;
-                hit.rec = f_as_u(h4.y);
-                hit.u = h4.z;
-                hit.v = h4.w;
-                if (hit.rec == kNone) {
-                    // shader.wgsl:1222-1231 — escaped into the environment.
+                emit_closest = true;
+                sts(&p.b.ray_d[slot], make_float4(so.next_dir.x, so.next_dir.y, so.next_dir.z, u_as_f(kNone)));
+                p.b.stage[slot] = STAGE_FLIGHT;
+                n_rays++;
+            }
+            sts(&p.b.pI[slot], I);
+            store_path(p, slot, s);
+        }
+        list_push(rayq, &c->ray_n[P], emit_closest, slot);
+        list_push(rayq, &c->ray_n[P], emit_shadow, slot | kShadowBit);
+    });
+    fast_flush_counts(0u, n_rays, n_shadow, p.counters);
+}
+
+#ifndef RT_WAVE_FINISH_MIN_BLOCKS
+#define RT_WAVE_FINISH_MIN_BLOCKS 8
+#endif
+
+// Slots whose ray escaped (sky light), whose path ended, or that are new: accumulate the
+// finished sample and start the pixel's next one.
+__global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wave_finish_kernel(const WaveParams p) {
+    const uint32_t P = p.wave & 1u;
+    WaveCtrl* c = p.b.ctrl;
+    uint32_t* rayq = p.b.rayq + (size_t)P * 2u * p.slots;
+    const float sin_half_fov = rt_sin(p.camera.fov_y / 2.0f);
+    const uint32_t sample_end = p.sample_begin + p.sample_count;
+    uint32_t n_paths = 0, n_rays = 0;
+    sweep_stage<kFinishThreads>(p, STAGE_FINISH, STAGE_FINISH_NEXT, STAGE_FINISH, [&](uint32_t slot, bool on) {
+        bool emit = false, retire = false;
+        if (on) {
+            uint4 I = lds(&p.b.pI[slot]);
+            PathRegs s;
+            uint32_t px = 0, py = 0;
+            if (I.w != SLOT_NEW) {
+                load_path(p, slot, s);
+                settle_shadow(p, slot, s);
+                if (I.w == SLOT_TRACED) {
+                    // shader.wgsl:1222-1231 — the ray escaped into the environment.
+                    const V3 d = xyz(lds(&p.b.ray_d[slot]));
                     float u, v;
                     direction_to_uv(d, u, v);
                     V3 sky = env_bilinear(p.env, u, v);
                     float pdf = env_direction_pdf(p.env, u, v);
-                    float w = power_heuristic(last_pdf, pdf);
-                    L = L + T * sky * w;
-                    finish = true;
-                } else {
-                    ShadeOut so;
-                    shade_hit(p.scene, p.env, o, d, hit, rng, T, L, so);
-                    bounce++;
-                    const bool done = so.done || bounce >= p.max_bounces;
-                    o = so.point;
-                    d = so.next_dir;
-                    last_pdf = so.next_pdf;
-                    pending = so.pending;
-                    if (so.want_shadow) {
-                        emit_shadow = true;
-                        sdir = so.shadow_dir;
-                        flags |= kFlagShadow;
-                        n_shadow++;
-                    }
-                    if (done) {
-                        if (emit_shadow) state = SLOT_ENDING;  // wait for the shadow ray, then finish
-                        else finish = true;
-                    } else {
-                        emit_closest = true;
-                    }
+                    float w = power_heuristic(s.last_pdf, pdf);
+                    s.L = s.L + s.T * sky * w;
+                }
+                // shader.wgsl:1367-1371: total += sample, alpha = 1. Only this slot touches the pixel.
+                pixel_of_id(p, I.x, px, py);
+                float4* a = p.accum + (size_t)py * p.width + px;
+                float4 v = *a;
+                v.x = v.x + s.L.x;
+                v.y = v.y + s.L.y;
+                v.z = v.z + s.L.z;
+                v.w = 1.0f;
+                *a = v;
+                I.y++;
+                if (I.y >= sample_end) {
+                    I.x += p.slot_stride;  // this pixel is complete: on to the slot's next one
+                    I.y = p.sample_begin;
                 }
             }
-        }
-        uint32_t px = 0, py = 0;
-        if (finish) {
-            // shader.wgsl:1367-1371: total += sample, alpha = 1. Only this slot touches the pixel.
-            pixel_of_id(p, I.x, px, py);
-            float4* a = p.accum + (size_t)py * p.width + px;
-            float4 v = *a;
-            v.x = v.x + L.x;
-            v.y = v.y + L.y;
-            v.z = v.z + L.z;
-            v.w = 1.0f;
-            *a = v;
-            I.y++;
-            if (I.y >= sample_end) {
-                I.x += p.slots;  // this pixel is complete: on to the slot's next one
-                I.y = p.sample_begin;
-            }
-            fresh = true;
-        }
-        if (fresh) {
             I.x = next_pixel_id(p, I.x, px, py);
             if (I.x == kNone) {
-                state = SLOT_RETIRED;
+                I.w = SLOT_RETIRED;
+                p.b.stage[slot] = STAGE_IDLE;
+                retire = true;
             } else {
-                const float sin_half_fov = rt_sin(p.camera.fov_y / 2.0f);
-                camera_ray(p.camera, sin_half_fov, px, py, p.width, p.height, I.y, rng, o, d);
+                V3 o, d;
+                camera_ray(p.camera, sin_half_fov, px, py, p.width, p.height, I.y, s.rng, o, d);
+                s.T = v3s(1.f);
+                s.L = v3s(0.f);
+                s.pending = v3s(0.f);
+                s.last_pdf = 1.0f;
+                s.flags = 0u;
+                I.z = 0u;
+                I.w = SLOT_TRACED;
+                sts(&p.b.ray_o[slot], make_float4(o.x, o.y, o.z, RT_INFINITY));
+                sts(&p.b.ray_d[slot], make_float4(d.x, d.y, d.z, u_as_f(kNone)));
+                p.b.stage[slot] = STAGE_FLIGHT;
+                store_path(p, slot, s);
+                emit = true;
                 n_paths++;
-                T = v3s(1.f);
-                L = v3s(0.f);
-                last_pdf = 1.0f;
-                bounce = 0u;
-                flags = 0u;
-                pending = v3s(0.f);
-                emit_closest = true;
-                emit_shadow = false;
-                state = SLOT_TRACED;
+                n_rays++;
             }
-        } else if (state != SLOT_ENDING) {
-            state = SLOT_TRACED;
+            sts(&p.b.pI[slot], I);
         }
-        if (emit_closest) n_rays++;
-        I.z = bounce;
-        I.w = state;
-        p.b.pI[slot] = I;
-        if (state != SLOT_RETIRED) {
-            p.b.pT[slot] = make_float4(T.x, T.y, T.z, last_pdf);
-            p.b.pL[slot] = make_float4(L.x, L.y, L.z, u_as_f(rng));
-            p.b.pP[slot] = make_float4(pending.x, pending.y, pending.z, u_as_f(flags));
-        }
-    }
+        list_push(rayq, &c->ray_n[P], emit, slot);
+        const unsigned gone = __ballot_sync(0xFFFFFFFFu, retire);
+        if (gone && (threadIdx.x & 31u) == 0u) atomicSub(&c->live, (uint32_t)__popc(gone));
+    });
+    fast_flush_counts(n_paths, n_rays, 0u, p.counters);
+}
 
-    // ---- pre-pass for the rays this wave emits: every lane of the warp together ----
-    if (emit_closest) {
+#ifndef RT_WAVE_PREPASS_MIN_BLOCKS
+#define RT_WAVE_PREPASS_MIN_BLOCKS 4
+#endif
+
+// Ray queue of this wave: the analytic pre-pass, one ray per thread, every lane busy.
+__global__ void __launch_bounds__(kPrepassThreads, RT_WAVE_PREPASS_MIN_BLOCKS) wave_prepass_kernel(const WaveParams p) {
+    __shared__ float4 spre[kPreMaxFloat4];
+    stage_pre(p.scene, spre);
+    const uint32_t P = p.wave & 1u;
+    WaveCtrl* c = p.b.ctrl;
+    if (!p.scene.hoisted) return;
+    const uint32_t count = c->ray_n[P];
+    uint32_t* rayq = p.b.rayq + (size_t)P * 2u * p.slots;
+    const uint32_t stride = gridDim.x * kPrepassThreads;
+    for (uint32_t i = blockIdx.x * kPrepassThreads + threadIdx.x; i < count; i += stride) {
+        const uint32_t e = rayq[i];
+        const uint32_t slot = e & ~kShadowBit;
+        const bool shadow = (e & kShadowBit) != 0u;
+        const V3 o = xyz(lds(&p.b.ray_o[slot]));
+        const V3 d = xyz(shadow ? lds(&p.b.sray_d[slot]) : lds(&p.b.ray_d[slot]));
         const RayCtx r = ray_setup(o, d);
         float t0_root;
         const bool root_ok = root_test(p.scene, r, t0_root);
         FHit best;
         Fallback fb;
         prepass(p.scene, spre, r, root_ok, best, fb);
-        p.b.ray_o[slot] = make_float4(o.x, o.y, o.z, best.t);
-        p.b.ray_d[slot] = make_float4(d.x, d.y, d.z, u_as_f(best.rec));
-        p.b.fb[slot] = make_float2(fb.t, u_as_f(fb.index));
-    } else if (emit_shadow) {
-        p.b.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);  // the shadow ray starts at the hit point
+        if (shadow) {
+            if (best.rec != kNone) {
+                sts(&p.b.occl[slot], 1u);
+                rayq[i] = kDeadEntry;  // settled: the walk skips it
+            }
+        } else {
+            p.b.ray_o[slot].w = best.t;
+            p.b.ray_d[slot].w = u_as_f(best.rec);
+            sts(&p.b.fb[slot], make_float2(fb.t, u_as_f(fb.index)));
+        }
     }
-    if (emit_shadow) {
-        const RayCtx r = ray_setup(o, sdir);
-        float t0_root;
-        const bool root_ok = root_test(p.scene, r, t0_root);
-        FHit best;
-        Fallback fb;
-        prepass(p.scene, spre, r, root_ok, best, fb);
-        shadow_blocked = best.rec != kNone;
-        p.b.occl[slot] = shadow_blocked ? 1u : 0u;
-        if (!shadow_blocked) p.b.sray_d[slot] = make_float4(sdir.x, sdir.y, sdir.z, 0.0f);
-    }
-    queue_push(p, ctrl, emit_closest, slot);
-    queue_push(p, ctrl, emit_shadow && !shadow_blocked, slot | kShadowBit);
-
-    // ---- bookkeeping ----
-    const unsigned live = __ballot_sync(0xFFFFFFFFu, state != SLOT_RETIRED);
-    if ((threadIdx.x & 31u) == 0u && live) atomicAdd(&ctrl->live, (uint32_t)__popc(live));
-    fast_flush_counts(n_paths, n_rays, n_shadow, p.counters);
 }
 
-#ifndef RT_WAVE_TRACE_MIN_BLOCKS
-#define RT_WAVE_TRACE_MIN_BLOCKS 4
+#ifndef RT_WAVE_WALK_MIN_BLOCKS
+#define RT_WAVE_WALK_MIN_BLOCKS 4
 #endif
 
 // The triangle walk of every queued ray. Persistent warps; a lane whose ray is finished
 // takes the next queue entry at the next round boundary.
-__global__ void __launch_bounds__(kTraceThreads, RT_WAVE_TRACE_MIN_BLOCKS) wave_trace_kernel(const WaveParams p) {
-    WaveCtrl* ctrl = p.b.ctrl + (p.wave & 1u);
-    const uint32_t total = ctrl->queued;
+__global__ void __launch_bounds__(kWalkThreads, RT_WAVE_WALK_MIN_BLOCKS) wave_walk_kernel(const WaveParams p) {
+    const uint32_t P = p.wave & 1u;
+    WaveCtrl* c = p.b.ctrl;
+    const uint32_t total = c->ray_n[P];
+    const uint32_t* rayq = p.b.rayq + (size_t)P * 2u * p.slots;
     const uint32_t lane = threadIdx.x & 31u;
     uint2 stack[kStackCap];
 
@@ -311,17 +439,17 @@ __global__ void __launch_bounds__(kTraceThreads, RT_WAVE_TRACE_MIN_BLOCKS) wave_
         if (idle && !drained) {
             const int leader = __ffs(idle) - 1;
             uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(&ctrl->head, (uint32_t)__popc(idle));
+            if ((int)lane == leader) base = atomicAdd(&c->ray_head[P], (uint32_t)__popc(idle));
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
             if (base + (uint32_t)__popc(idle) >= total) drained = true;
             if (!busy) {
                 const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
-                if (idx < total) {
-                    const uint32_t e = p.b.queue[idx];
+                const uint32_t e = idx < total ? rayq[idx] : kDeadEntry;
+                if (e != kDeadEntry) {
                     slot = e & ~kShadowBit;
                     any_hit = (e & kShadowBit) != 0u;
-                    const float4 o4 = p.b.ray_o[slot];
-                    const float4 d4 = any_hit ? p.b.sray_d[slot] : p.b.ray_d[slot];
+                    const float4 o4 = lds(&p.b.ray_o[slot]);
+                    const float4 d4 = any_hit ? lds(&p.b.sray_d[slot]) : lds(&p.b.ray_d[slot]);
                     r = ray_setup(xyz(o4), xyz(d4));
                     best.t = any_hit ? RT_INFINITY : o4.w;
                     best.rec = any_hit ? kNone : f_as_u(d4.w);
@@ -333,25 +461,31 @@ __global__ void __launch_bounds__(kTraceThreads, RT_WAVE_TRACE_MIN_BLOCKS) wave_
                 }
             }
         }
-        if (!__any_sync(0xFFFFFFFFu, busy)) break;
+        if (!__any_sync(0xFFFFFFFFu, busy)) {
+            if (drained) break;
+            continue;  // only dead entries came back: fetch again
+        }
 
         // ---- one round of the walk: interior records, then the leaf ----
         while (busy && w.cur < kLeafBit) walk_node(p.scene, r, w, stack);
         bool settled = false;
         if (busy && w.cur != kNone) settled = walk_leaf(p.scene, r, any_hit, best, w, stack);
-        if (busy && (settled || w.cur == kNone)) {
-            // ---- this lane's ray is finished ----
+
+        // ---- lanes whose ray is finished hand over their result ----
+        const bool finished = busy && (settled || w.cur == kNone);
+        if (finished) {
             if (any_hit) {
-                if (best.rec != kNone) p.b.occl[slot] = 1u;
+                if (best.rec != kNone) sts(&p.b.occl[slot], 1u);
             } else {
                 if (best.rec == kNone) {
-                    const float2 f = p.b.fb[slot];
+                    const float2 f = lds(&p.b.fb[slot]);
                     Fallback fb;
                     fb.t = f.x;
                     fb.index = f_as_u(f.y);
                     resolve_fallback(p.scene, r, fb, best);
                 }
-                p.b.hit[slot] = make_float4(best.t, u_as_f(best.rec), best.u, best.v);
+                sts(&p.b.hit[slot], make_float4(best.t, u_as_f(best.rec), best.u, best.v));
+                p.b.stage[slot] = best.rec != kNone ? STAGE_SHADE : STAGE_FINISH;
             }
             busy = false;
         }
