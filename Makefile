@@ -28,7 +28,7 @@ $(PKG)/librt_host.so: $(HOST_SRC) $(HOST_HDR)
 
 backend: $(PKG)/librt_backend.so
 $(PKG)/librt_backend.so: $(PKG)/csrc/rt_backend.cu $(wildcard $(PKG)/csrc/*.cuh) include/rt_backend.h include/rt_types.h
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(PKG)/csrc/rt_backend.cu -ldl 2> $(PKG)/csrc/ptxas.log || (cat $(PKG)/csrc/ptxas.log; false)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(PKG)/csrc/rt_backend.cu -ldl -lpthread 2> $(PKG)/csrc/ptxas.log || (cat $(PKG)/csrc/ptxas.log; false)
 	@grep -E "registers|spill|error" $(PKG)/csrc/ptxas.log | head -40 || true
 
 cli: $(PKG)/rt_render

@@ -14,11 +14,15 @@ value      = rays traced by all ranks / device time (CUDA events on the launch s
 e2e        = same metric through the public API with HOST buffers inside the timed
              region: scene + camera upload (host -> device), render, reduce, and the
              device -> host read of the W*H*4-float accumulation buffer.
-roofline   = algorithmic bytes of the render launch (SURVEY §8d formula over exact
-             in-kernel work counters of the same workload) / event time, against the
-             measured HBM copy bandwidth in MEASURED_PEAKS.json. The working set of this
-             scene is L1/L2 resident, so `traffic` (DRAM bytes) is far below it; the
-             issue-rate view is reported beside it as `roofline_issue`.
+roofline   = the dominant kernel, wave_walk_kernel (BVH walk): algorithmic bytes of the
+             traversal (32 B per box test + 48 B per triangle test, counted
+             exactly by the reference-order kernel on the same workload, untimed) per
+             launch / the kernel's average launch duration, measured with CUDA events
+             around every launch of the timed region (rt_set_profiling), against the
+             measured HBM copy bandwidth in MEASURED_PEAKS.json. The scene itself is
+             L1/L2 resident; the kernel is issue-bound, which `roofline_issue` (whole
+             step, algorithmic FP32 operations against 148 SM x 128 lanes x 2 x f_SM)
+             and `roofline_step` (all algorithmic bytes of the step) put beside it.
 cpu_baseline / --impl reference = the C++ oracle (a restatement of shader.wgsl; the Rust
              + wgpu reference cannot be built or run in this image) on all host cores.
 """
@@ -63,6 +67,11 @@ def algorithmic_bytes(c, pixels):
     return (32 * c["nodes_tested"] + 48 * c["tris_tested"] + 16 * c["spheres_tested"] +
             64 * c["planes_tested"] + 48 * c["tri_hits"] + 16 * c["hits"] +
             shaded * (2 * 16) + c["env_lookups"] * (4 * 16) + 32 * pixels)
+
+
+def traversal_bytes(c):
+    """The walk kernel's share of algorithmic_bytes: box tests + triangle tests."""
+    return 32 * c["nodes_tested"] + 48 * c["tris_tested"]
 
 
 def algorithmic_flops(c):
@@ -263,6 +272,16 @@ def main():
         step_ms.append(es.elapsed_time(e2))
         kernel_ms.append(e0.elapsed_time(e1))
     launches = state.launch_count() - launches_before
+    # One more step of the same region with CUDA events around every kernel launch
+    # (rt_set_profiling): per-kernel durations for the roofline. Kept out of `value`'s
+    # steps because creating ~10^4 events per step slows the host's launch loop.
+    state.set_profiling(True)
+    flush.fill_(1)
+    barrier()
+    device_step()
+    barrier()
+    profile = state.profile()
+    state.set_profiling(False)
     clocks = sampler.stop() if sampler else None
 
     # ---- timed: end to end with host buffers ----
@@ -309,13 +328,26 @@ def main():
             sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         else:
             hbm_peak, peak_src, sm_max = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)", 1965.0
-        launch_s = total_kernel_ms / args.steps * 1e-3  # rank-0 view of one render launch
+        render_s = total_kernel_ms / args.steps * 1e-3  # rank-0 view of one render (all its launches)
         alg_bytes = algorithmic_bytes(counters, pixels)
         alg_flops = algorithmic_flops(counters)
-        achieved_gbs = alg_bytes / launch_s / 1e9
         sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
         fp32_peak = SM_COUNT * FP32_LANES * 2 * sm_mhz * 1e6 / 1e12
-        achieved_tf = alg_flops / launch_s / 1e12
+        achieved_tf = alg_flops / render_s / 1e12
+        # dominant kernel = the one with the largest share of the profiled device time
+        kernels = profile["kernels"]
+        kernel_total_ms = sum(k["ms"] for k in kernels.values()) or 1.0
+        walk = kernels["wave_walk_kernel"]
+        walk_launches = max(1, walk["launches"])
+        walk_launch_s = walk["ms"] / walk_launches * 1e-3
+        walk_bytes_per_launch = traversal_bytes(counters) * profile["renders"] / walk_launches
+        achieved_gbs = walk_bytes_per_launch / walk_launch_s / 1e9 if walk_launch_s > 0 else 0.0
+        traffic, traffic_note = None, "no ncu capture committed"
+        tpath = os.path.join(ROOT, "profiles", "walk_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("note", "")
 
         out = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": n_gpus,
@@ -334,14 +366,23 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": None,
-                         "peak_source": peak_src, "kernel": "render_kernel",
-                         "algorithmic_bytes_per_launch": int(alg_bytes),
-                         "launch_ms": launch_s * 1e3,
-                         "note": "working set is L1/L2 resident; see roofline_issue"},
+                         "frac": achieved_gbs / hbm_peak, "traffic": traffic,
+                         "peak_source": peak_src, "kernel": "wave_walk_kernel",
+                         "kernel_share_of_device_time": walk["ms"] / kernel_total_ms,
+                         "algorithmic_bytes_per_launch": int(walk_bytes_per_launch),
+                         "launch_ms": walk_launch_s * 1e3, "launches_per_step": walk_launches // max(1, profile["renders"]),
+                         "traffic_note": traffic_note,
+                         "note": "scene is L1/L2 resident and the walk is issue-bound (see roofline_issue); "
+                                 "DRAM traffic is the ray / hit records of the wavefront, not scene data"},
+            "roofline_step": {"bound": "hbm", "achieved": alg_bytes / render_s / 1e9, "peak": hbm_peak,
+                              "unit": "GB/s", "frac": alg_bytes / render_s / 1e9 / hbm_peak,
+                              "algorithmic_bytes_per_step": int(alg_bytes), "render_ms": render_s * 1e3},
             "roofline_issue": {"bound": "fp32-issue", "achieved": achieved_tf, "peak": fp32_peak,
                                "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
-                               "sm_mhz": sm_mhz, "algorithmic_flops_per_launch": int(alg_flops)},
+                               "sm_mhz": sm_mhz, "algorithmic_flops_per_step": int(alg_flops)},
+            "kernel_profile": {"waves_per_step": profile["waves"] // max(1, profile["renders"]),
+                               "gap_ms_per_step": profile["gap_ms"] / max(1, profile["renders"]),
+                               "ms_per_step": {k: v["ms"] / max(1, profile["renders"]) for k, v in kernels.items()}},
             "counters_per_step_rank0": counters,
         }
         if not args.no_cpu_baseline:

@@ -79,7 +79,10 @@ int rt_clear(RtContext* ctx);
  * sample_count - 1 (these values seed the per-pixel RNG, shader.wgsl:1309-1312).
  * Accumulates into the accumulation buffer exactly like shader.wgsl:1367-1371.
  * max_bounces is the reference's MAX_BOUNCES (10, shader.wgsl:232) made a parameter.
- * Asynchronous: work is enqueued on the context's stream. */
+ * Work is enqueued on the context's stream and ordered with everything else on it. The
+ * call paces the wavefront pipeline from the host (it reads a live-path counter one chunk
+ * of waves behind the launches), so it returns when the last waves have been queued —
+ * close to completion; use rt_sync / rt_read_accum to wait for the result. */
 int rt_render(RtContext* ctx, uint32_t sample_begin, uint32_t sample_count, uint32_t max_bounces,
               uint32_t environment_index);
 
@@ -100,6 +103,20 @@ int rt_write_accum(RtContext* ctx, const float* rgba_in);
  * src/hdr.rs:203-216), ACES fit with magenta for negatives (src/shaders/hdr.wgsl:3-22),
  * sRGB encode (surface format, src/hdr.rs:120). rgb8_out is W*H*3 host bytes. */
 int rt_tonemap_rgb8(RtContext* ctx, uint32_t sample_total, uint8_t* rgb8_out);
+
+/* Per-kernel device time of the wavefront pipeline (CUDA events around every launch on the
+ * launching stream), accumulated over rt_render calls while profiling is enabled. Kernel
+ * order: shade, finish, pre-pass, walk (rsoderh-raytracing_b200/csrc/rt_wave.cuh). */
+typedef struct RtWaveProfile {
+    uint64_t renders;       /* rt_render calls measured                      */
+    uint64_t waves;         /* waves launched (including trailing empty ones) */
+    uint64_t launches[4];   /* kernel launches per kind                       */
+    double kernel_ms[4];    /* summed device time per kind                    */
+    double gap_ms;          /* time between a wave's last kernel and the next wave's first */
+    double total_ms;        /* first launch to last completion, summed over renders */
+} RtWaveProfile;
+int rt_set_profiling(RtContext* ctx, int enabled);   /* also clears the accumulated profile */
+int rt_get_profile(RtContext* ctx, RtWaveProfile* out);
 
 int rt_set_detailed_counters(RtContext* ctx, int enabled);
 int rt_reset_counters(RtContext* ctx);

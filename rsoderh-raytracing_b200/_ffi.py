@@ -135,6 +135,19 @@ HOST_SIGNATURES = {
     "rt_free": (None, [_vp]),
 }
 
+class RtWaveProfile(C.Structure):
+    """include/rt_backend.h RtWaveProfile. Kernel order: shade, finish, pre-pass, walk."""
+    KERNELS = ("wave_shade_kernel", "wave_finish_kernel", "wave_prepass_kernel", "wave_walk_kernel")
+    _fields_ = [("renders", C.c_uint64), ("waves", C.c_uint64), ("launches", C.c_uint64 * 4),
+                ("kernel_ms", C.c_double * 4), ("gap_ms", C.c_double), ("total_ms", C.c_double)]
+
+    def as_dict(self):
+        return {"renders": int(self.renders), "waves": int(self.waves), "gap_ms": float(self.gap_ms),
+                "total_ms": float(self.total_ms),
+                "kernels": {k: {"launches": int(self.launches[i]), "ms": float(self.kernel_ms[i])}
+                            for i, k in enumerate(self.KERNELS)}}
+
+
 BACKEND_SIGNATURES = {
     "rt_backend_version": (C.c_char_p, []),
     "rt_device_count": (C.c_int, [C.POINTER(C.c_int)]),
@@ -154,6 +167,8 @@ BACKEND_SIGNATURES = {
     "rt_read_accum": (C.c_int, [_vp, _vp]),
     "rt_write_accum": (C.c_int, [_vp, _vp]),
     "rt_tonemap_rgb8": (C.c_int, [_vp, _u32, _vp]),
+    "rt_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "rt_get_profile": (C.c_int, [_vp, C.POINTER(RtWaveProfile)]),
     "rt_set_detailed_counters": (C.c_int, [_vp, C.c_int]),
     "rt_reset_counters": (C.c_int, [_vp]),
     "rt_get_counters": (C.c_int, [_vp, C.POINTER(RtCounters)]),

@@ -424,6 +424,15 @@ class State:
     def set_detailed_counters(self, enabled: bool):
         self._check(self._lib.rt_set_detailed_counters(self._ctx, int(enabled)))
 
+    def set_profiling(self, enabled: bool):
+        """Per-kernel CUDA-event timing of the wavefront pipeline (clears the profile)."""
+        self._check(self._lib.rt_set_profiling(self._ctx, int(enabled)))
+
+    def profile(self) -> dict:
+        prof = _ffi.RtWaveProfile()
+        self._check(self._lib.rt_get_profile(self._ctx, C.byref(prof)))
+        return prof.as_dict()
+
     def reset_counters(self):
         self._check(self._lib.rt_reset_counters(self._ctx))
 

@@ -18,6 +18,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rt_backend.h"
@@ -398,18 +399,17 @@ struct RtContext {
     enum Kernel { KERNEL_WAVE, KERNEL_FAST, KERNEL_PIXEL, KERNEL_POOL };
     Kernel kernel = KERNEL_WAVE;
     // wavefront pipeline state (rt_wave.cuh)
-    static constexpr int kWaveMaxGroups = 4;
-    rtw::WaveBuffers wave[kWaveMaxGroups]{};
+    rtw::WaveBuffers wave{};
     void* wave_arena = nullptr;
-    uint32_t wave_slots = 0;       // per-group capacity the arena was allocated for
-    int wave_arena_groups = 0;
-    uint32_t wave_max_slots = 2048u * 1024u;  // all groups together
-    int wave_groups = 1;           // independent slot groups whose waves may overlap on the device
-    int wave_walk_blocks_per_sm = 0;  // 0 = RT_WAVE_WALK_MIN_BLOCKS split over the groups
-    uint32_t* wave_live_host = nullptr;  // pinned read-back of WaveCtrl::live: [2 chunks in flight][groups]
-    cudaStream_t wave_streams[kWaveMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t wave_events[2][kWaveMaxGroups] = {};
-    cudaEvent_t wave_fork = nullptr;
+    uint32_t wave_slots = 0;          // capacity the arena was allocated for
+    uint32_t wave_max_slots = 8192u * 1024u;
+    void* wave_staging = nullptr;     // per-sample radiance planes of the current batch
+    size_t wave_staging_bytes = 0;
+    size_t wave_staging_budget = (size_t)2048 << 20;
+    uint32_t* wave_live_host = nullptr;  // pinned read-back of WaveCtrl::live, one word per chunk in flight
+    cudaEvent_t wave_events[2] = {nullptr, nullptr};
+    bool profiling = false;
+    RtWaveProfile profile{};
     bool pool_launched = false;
     bool detailed = false;
     uint64_t launches = 0;
@@ -514,19 +514,17 @@ bool validate_bvh(const RtSceneDesc& s, uint32_t* depth_out, std::string* why) {
 }
 
 // ---- wavefront pipeline (rt_wave.cuh): buffers and the wave loop ----
-int wave_reserve(RtContext* ctx, uint32_t slots, int groups) {
-    if (ctx->wave_arena && ctx->wave_slots >= slots && ctx->wave_arena_groups == groups) return RT_OK;
-    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->wave_arena);
-    ctx->wave_arena = nullptr;
-    ctx->wave_slots = 0;
-    const size_t S = slots;
-    // per group: 8 x 16-byte arrays + fb (8) + occl (4) + rayq (4 x 4) + stage (1) + ctrl
-    const size_t per_group = ((S * (8 * 16 + 8 + 4 + 16 + 1) + 512) + 255) & ~(size_t)255;
-    RT_CUDA(ctx, cudaMalloc(&ctx->wave_arena, per_group * (size_t)groups));
-    for (int g = 0; g < groups; g++) {
-        char* q = (char*)ctx->wave_arena + per_group * (size_t)g;
-        rtw::WaveBuffers& b = ctx->wave[g];
+int wave_reserve(RtContext* ctx, uint32_t slots, size_t staging_bytes) {
+    if (!(ctx->wave_arena && ctx->wave_slots >= slots)) {
+        RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->wave_arena);
+        ctx->wave_arena = nullptr;
+        ctx->wave_slots = 0;
+        const size_t S = slots;
+        // 8 x 16-byte arrays + fb (8) + occl (4) + rayq (4 x 4) + stage (1) + ctrl
+        RT_CUDA(ctx, cudaMalloc(&ctx->wave_arena, S * (8 * 16 + 8 + 4 + 16 + 1) + 512));
+        char* q = (char*)ctx->wave_arena;
+        rtw::WaveBuffers& b = ctx->wave;
         b.ray_o = (float4*)q;  q += S * 16;
         b.ray_d = (float4*)q;  q += S * 16;
         b.sray_d = (float4*)q; q += S * 16;
@@ -541,76 +539,71 @@ int wave_reserve(RtContext* ctx, uint32_t slots, int groups) {
         b.stage = (uint8_t*)q; q += S;
         q = (char*)(((uintptr_t)q + 63) & ~(uintptr_t)63);
         b.ctrl = (rtw::WaveCtrl*)q;
+        ctx->wave_slots = slots;
     }
-    ctx->wave_slots = slots;
-    ctx->wave_arena_groups = groups;
+    if (!(ctx->wave_staging && ctx->wave_staging_bytes >= staging_bytes)) {
+        RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->wave_staging);
+        ctx->wave_staging = nullptr;
+        ctx->wave_staging_bytes = 0;
+        RT_CUDA(ctx, cudaMalloc(&ctx->wave_staging, staging_bytes));
+        ctx->wave_staging_bytes = staging_bytes;
+    }
     return RT_OK;
 }
 
-// Runs waves until every slot has retired. The slots are split into independent groups,
-// each on its own stream, so one group's memory-bound shading overlaps another's
-// issue-bound walk. The host only paces the launches: it reads the live-slot counts one
-// chunk behind the launches, so the streams never run dry.
+// Renders the sample range in batches. Inside a batch the paths are independent work items
+// handed to the slots as they free up; waves run until every slot has retired, then the
+// staged samples are added to the accumulation buffer in sample order. The host only paces
+// the launches: it reads the live-slot count one chunk behind, so the stream never runs dry.
 int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, uint32_t sample_count,
                 uint32_t max_bounces) {
-    rtw::WaveParams base;
-    memset(&base, 0, sizeof base);
-    base.scene = ctx->fast;
-    base.env.texture = e.texture;
-    base.env.alias = e.d_alias;
-    base.env.width = e.width;
-    base.env.height = e.height;
-    base.camera = ctx->camera;
-    base.accum = ctx->d_accum;
-    base.counters = ctx->d_counters;
-    base.width = ctx->width;
-    base.height = ctx->height;
-    base.tiles_x = (ctx->width + 7u) / 8u;
-    base.pixel_ids = base.tiles_x * ((ctx->height + 7u) / 8u) * 64u;
-    base.sample_begin = sample_begin;
-    base.sample_count = sample_count;
-    base.max_bounces = max_bounces;
+    rtw::WaveParams p;
+    memset(&p, 0, sizeof p);
+    p.scene = ctx->fast;
+    p.env.texture = e.texture;
+    p.env.alias = e.d_alias;
+    p.env.width = e.width;
+    p.env.height = e.height;
+    p.camera = ctx->camera;
+    p.accum = ctx->d_accum;
+    p.counters = ctx->d_counters;
+    p.width = ctx->width;
+    p.height = ctx->height;
+    p.tiles_x = (ctx->width + 7u) / 8u;
+    p.pixel_ids = p.tiles_x * ((ctx->height + 7u) / 8u) * 64u;
+    p.max_bounces = max_bounces;
 
-    const uint32_t total_slots = base.pixel_ids < ctx->wave_max_slots ? base.pixel_ids : ctx->wave_max_slots;
-    int groups = ctx->wave_groups;
-    while (groups > 1 && total_slots / (uint32_t)groups < 32768u) groups--;  // small frames: no point splitting
-    const uint32_t per_group = (total_slots + (uint32_t)groups - 1u) / (uint32_t)groups;
-    int st = wave_reserve(ctx, per_group, groups);
+    // Batch size: as many samples as the staging budget holds, and path indices must fit 32 bits.
+    const size_t pixels = (size_t)ctx->width * ctx->height;
+    uint64_t batch = ctx->wave_staging_budget / (pixels * sizeof(float4));
+    const uint64_t index_cap = 0xFFFF0000ull / p.pixel_ids;
+    if (batch > index_cap) batch = index_cap;
+    if (batch > sample_count) batch = sample_count;
+    if (batch < 1) batch = 1;
+    const uint64_t paths_per_batch = (uint64_t)p.pixel_ids * batch;
+    p.slots = (uint32_t)(paths_per_batch < ctx->wave_max_slots ? paths_per_batch : ctx->wave_max_slots);
+    int st = wave_reserve(ctx, p.slots, pixels * sizeof(float4) * (size_t)batch);
     if (st != RT_OK) return st;
+    p.b = ctx->wave;
+    p.staging = (float4*)ctx->wave_staging;
 
-    rtw::WaveParams p[RtContext::kWaveMaxGroups];
-    for (int g = 0; g < groups; g++) {
-        p[g] = base;
-        p[g].b = ctx->wave[g];
-        p[g].slot_base = per_group * (uint32_t)g;
-        p[g].slot_stride = per_group * (uint32_t)groups;
-        p[g].slots = per_group;
-    }
     auto blocks_for = [&](uint32_t items, int threads, int per_sm) {
         unsigned need = (items + (unsigned)threads - 1u) / (unsigned)threads;
         unsigned cap = (unsigned)ctx->sm_count * (unsigned)per_sm;
         return need < cap ? (need ? need : 1u) : cap;
     };
-    auto split = [&](int per_sm) { return (per_sm + groups - 1) / groups; };
-    const int walk_per_sm = ctx->wave_walk_blocks_per_sm ? ctx->wave_walk_blocks_per_sm : split(RT_WAVE_WALK_MIN_BLOCKS);
-    const unsigned shade_blocks = blocks_for(per_group, rtw::kShadeThreads, split(RT_WAVE_SHADE_MIN_BLOCKS));
-    const unsigned finish_blocks = blocks_for(per_group, rtw::kFinishThreads, split(RT_WAVE_FINISH_MIN_BLOCKS));
-    const unsigned prepass_blocks = blocks_for(2u * per_group, rtw::kPrepassThreads, split(RT_WAVE_PREPASS_MIN_BLOCKS));
-    const unsigned walk_blocks = blocks_for(2u * per_group, rtw::kWalkThreads, walk_per_sm);
+    const unsigned shade_blocks = blocks_for(p.slots, rtw::kShadeThreads, RT_WAVE_SHADE_MIN_BLOCKS);
+    const unsigned finish_blocks = blocks_for(p.slots, rtw::kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS);
+    const unsigned prepass_blocks = blocks_for(2u * p.slots, rtw::kPrepassThreads, RT_WAVE_PREPASS_MIN_BLOCKS);
+    const unsigned walk_blocks = blocks_for(2u * p.slots, rtw::kWalkThreads, RT_WAVE_WALK_MIN_BLOCKS);
+    cudaStream_t s = ctx->stream;
 
-    // fork: the group streams start after everything queued on the context's stream
-    RT_CUDA(ctx, cudaEventRecord(ctx->wave_fork, ctx->stream));
-    for (int g = 0; g < groups; g++) {
-        RT_CUDA(ctx, cudaStreamWaitEvent(ctx->wave_streams[g], ctx->wave_fork, 0));
-        rtw::wave_init_kernel<<<(per_group + 255) / 256, 256, 0, ctx->wave_streams[g]>>>(p[g]);
-        ctx->launches++;
-    }
-    RT_CUDA(ctx, cudaGetLastError());
-
-    // RT_WAVE_TIMELINE=1 (diagnostics): CUDA events around every kernel of group 0.
-    static const bool timeline = getenv("RT_WAVE_TIMELINE") != nullptr;
+    // RT_WAVE_TIMELINE=1 (diagnostics) or rt_set_profiling: CUDA events around every kernel.
+    static const bool timeline_print = getenv("RT_WAVE_TIMELINE") != nullptr;
+    const bool timeline = timeline_print || ctx->profiling;
     std::vector<cudaEvent_t> tl;
-    auto mark = [&](cudaStream_t s) {
+    auto mark = [&]() {
         if (!timeline) return;
         cudaEvent_t ev;
         cudaEventCreate(&ev);
@@ -618,56 +611,58 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
         tl.push_back(ev);
     };
 
-    const uint32_t chunk = 16;
-    uint32_t wave = 0;
     int status = RT_OK;
-    for (uint32_t k = 0;; k++) {
-        for (uint32_t i = 0; i < chunk; i++, wave++) {
-            for (int g = 0; g < groups; g++) {
-                cudaStream_t s = ctx->wave_streams[g];
-                p[g].wave = wave;
-                if (g == 0) mark(s);
-                rtw::wave_shade_kernel<<<shade_blocks, rtw::kShadeThreads, 0, s>>>(p[g]);
-                if (g == 0) mark(s);
-                rtw::wave_finish_kernel<<<finish_blocks, rtw::kFinishThreads, 0, s>>>(p[g]);
-                if (g == 0) mark(s);
-                rtw::wave_prepass_kernel<<<prepass_blocks, rtw::kPrepassThreads, 0, s>>>(p[g]);
-                if (g == 0) mark(s);
-                rtw::wave_walk_kernel<<<walk_blocks, rtw::kWalkThreads, 0, s>>>(p[g]);
-                if (g == 0) mark(s);
+    for (uint32_t done = 0; done < sample_count && status == RT_OK; done += (uint32_t)batch) {
+        p.batch_begin = sample_begin + done;
+        p.batch_count = (uint32_t)(sample_count - done < batch ? sample_count - done : batch);
+        p.path_total = p.pixel_ids * p.batch_count;
+        rtw::wave_init_kernel<<<(p.slots + 255) / 256, 256, 0, s>>>(p);
+        ctx->launches++;
+
+        const uint32_t chunk = 8;
+        uint32_t wave = 0;
+        for (uint32_t k = 0;; k++) {
+            for (uint32_t i = 0; i < chunk; i++, wave++) {
+                p.wave = wave;
+                mark();
+                rtw::wave_shade_kernel<<<shade_blocks, rtw::kShadeThreads, 0, s>>>(p);
+                mark();
+                rtw::wave_finish_kernel<<<finish_blocks, rtw::kFinishThreads, 0, s>>>(p);
+                mark();
+                rtw::wave_prepass_kernel<<<prepass_blocks, rtw::kPrepassThreads, 0, s>>>(p);
+                mark();
+                rtw::wave_walk_kernel<<<walk_blocks, rtw::kWalkThreads, 0, s>>>(p);
+                mark();
                 ctx->launches += 4;
             }
-        }
-        cudaError_t ce = cudaGetLastError();
-        for (int g = 0; g < groups && ce == cudaSuccess; g++) {
-            ce = cudaMemcpyAsync(&ctx->wave_live_host[(k & 1u) * RtContext::kWaveMaxGroups + g], &p[g].b.ctrl->live,
-                                 sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->wave_streams[g]);
-            if (ce == cudaSuccess) ce = cudaEventRecord(ctx->wave_events[k & 1u][g], ctx->wave_streams[g]);
-        }
-        if (ce != cudaSuccess) {
-            status = fail(ctx, RT_ERR_CUDA, "wave launch failed: %s", cudaGetErrorString(ce));
-            break;
-        }
-        if (k > 0) {
-            uint32_t live = 0;
-            for (int g = 0; g < groups; g++) {
-                ce = cudaEventSynchronize(ctx->wave_events[(k - 1u) & 1u][g]);
-                if (ce != cudaSuccess) break;
-                live += ctx->wave_live_host[((k - 1u) & 1u) * RtContext::kWaveMaxGroups + g];
+            cudaError_t ce = cudaGetLastError();
+            if (ce == cudaSuccess)
+                ce = cudaMemcpyAsync(&ctx->wave_live_host[k & 1u], &p.b.ctrl->live, sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, s);
+            if (ce == cudaSuccess) ce = cudaEventRecord(ctx->wave_events[k & 1u], s);
+            if (ce == cudaSuccess && k > 0) {
+                ce = cudaEventSynchronize(ctx->wave_events[(k - 1u) & 1u]);
+                if (ce == cudaSuccess && ctx->wave_live_host[(k - 1u) & 1u] == 0u) break;  // the last chunk ran empty
             }
             if (ce != cudaSuccess) {
-                status = fail(ctx, RT_ERR_CUDA, "wave synchronisation failed: %s", cudaGetErrorString(ce));
+                status = fail(ctx, RT_ERR_CUDA, "wave launch failed: %s", cudaGetErrorString(ce));
                 break;
             }
-            if (live == 0u) break;  // the chunk after it only ran empty waves
+            if (wave > 0x7FFFFF00u) {
+                status = fail(ctx, RT_ERR_STATE, "wave loop did not terminate");
+                break;
+            }
         }
-        if (wave > 0x7FFFFF00u) {
-            status = fail(ctx, RT_ERR_STATE, "wave loop did not terminate");
-            break;
+        if (status == RT_OK) {
+            rtw::wave_accumulate_kernel<<<(unsigned)((pixels + 255) / 256), 256, 0, s>>>(p);
+            ctx->launches++;
+            cudaError_t ce = cudaGetLastError();
+            if (ce != cudaSuccess) status = fail(ctx, RT_ERR_CUDA, "accumulate launch failed: %s", cudaGetErrorString(ce));
         }
     }
+
     if (timeline && !tl.empty()) {
-        cudaStreamSynchronize(ctx->wave_streams[0]);
+        cudaStreamSynchronize(s);
         double sum[5] = {0, 0, 0, 0, 0};
         float total = 0.f;
         cudaEventElapsedTime(&total, tl.front(), tl.back());
@@ -684,20 +679,25 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
                 sum[4] += ms;
             }
         }
-        fprintf(stderr, "[wave timeline] waves=%zu total=%.3f ms | shade %.3f finish %.3f prepass %.3f walk %.3f gaps %.3f ms\n",
-                waves, total, sum[0], sum[1], sum[2], sum[3], sum[4]);
-        for (size_t w = 0; w < waves; w += (waves / 12 ? waves / 12 : 1)) {
-            float t[4];
-            for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], tl[w * 5 + j], tl[w * 5 + j + 1]);
-            fprintf(stderr, "   wave %4zu: shade %7.1f finish %7.1f prepass %7.1f walk %7.1f us\n", w, t[0] * 1e3, t[1] * 1e3,
-                    t[2] * 1e3, t[3] * 1e3);
+        ctx->profile.renders++;
+        ctx->profile.waves += waves;
+        for (int j = 0; j < 4; j++) {
+            ctx->profile.launches[j] += waves;
+            ctx->profile.kernel_ms[j] += sum[j];
+        }
+        ctx->profile.gap_ms += sum[4];
+        ctx->profile.total_ms += total;
+        if (timeline_print) {
+            fprintf(stderr, "[wave timeline] slots=%u waves=%zu total=%.3f ms | shade %.3f finish %.3f prepass %.3f walk %.3f gaps %.3f ms\n",
+                    p.slots, waves, total, sum[0], sum[1], sum[2], sum[3], sum[4]);
+            for (size_t w = 0; w < waves; w += (waves / 12 ? waves / 12 : 1)) {
+                float t[4];
+                for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], tl[w * 5 + j], tl[w * 5 + j + 1]);
+                fprintf(stderr, "   wave %4zu: shade %7.1f finish %7.1f prepass %7.1f walk %7.1f us\n", w, t[0] * 1e3,
+                        t[1] * 1e3, t[2] * 1e3, t[3] * 1e3);
+            }
         }
         for (cudaEvent_t ev : tl) cudaEventDestroy(ev);
-    }
-    // join: later work on the context's stream waits for every group
-    for (int g = 0; g < groups; g++) {
-        cudaEventRecord(ctx->wave_events[0][g], ctx->wave_streams[g]);
-        cudaStreamWaitEvent(ctx->stream, ctx->wave_events[0][g], 0);
     }
     return status;
 }
@@ -810,26 +810,15 @@ int rt_create(int device, RtContext** out) {
         long v = atol(k);
         if (v >= 1024 && v <= (1l << 24)) ctx->wave_max_slots = (uint32_t)v;
     }
-    if (const char* k = getenv("RT_WAVE_GROUPS")) {
-        int v = atoi(k);
-        if (v >= 1 && v <= RtContext::kWaveMaxGroups) ctx->wave_groups = v;
+    if (const char* k = getenv("RT_WAVE_STAGING_MB")) {
+        long v = atol(k);
+        if (v >= 1 && v <= (1l << 18)) ctx->wave_staging_budget = (size_t)v << 20;
     }
-    if (const char* k = getenv("RT_WAVE_WALK_BLOCKS")) {
-        int v = atoi(k);
-        if (v >= 1 && v <= 8) ctx->wave_walk_blocks_per_sm = v;
-    }
-    if ((e = cudaHostAlloc(&ctx->wave_live_host, 2 * RtContext::kWaveMaxGroups * sizeof(uint32_t),
-                           cudaHostAllocDefault)) != cudaSuccess)
+    if ((e = cudaHostAlloc(&ctx->wave_live_host, 2 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess)
         return bail("cudaHostAlloc", e);
-    for (int g = 0; g < RtContext::kWaveMaxGroups; g++) {
-        if ((e = cudaStreamCreateWithFlags(&ctx->wave_streams[g], cudaStreamNonBlocking)) != cudaSuccess)
-            return bail("cudaStreamCreate", e);
-        for (int i = 0; i < 2; i++)
-            if ((e = cudaEventCreateWithFlags(&ctx->wave_events[i][g], cudaEventDisableTiming)) != cudaSuccess)
-                return bail("cudaEventCreate", e);
-    }
-    if ((e = cudaEventCreateWithFlags(&ctx->wave_fork, cudaEventDisableTiming)) != cudaSuccess)
-        return bail("cudaEventCreate", e);
+    for (int i = 0; i < 2; i++)
+        if ((e = cudaEventCreateWithFlags(&ctx->wave_events[i], cudaEventDisableTiming)) != cudaSuccess)
+            return bail("cudaEventCreate", e);
     *out = ctx;
     return RT_OK;
 }
@@ -846,12 +835,9 @@ void rt_destroy(RtContext* ctx) {
     cudaFree(ctx->d_stack_scratch);
     cudaFree(ctx->wave_arena);
     if (ctx->wave_live_host) cudaFreeHost(ctx->wave_live_host);
-    for (int g = 0; g < RtContext::kWaveMaxGroups; g++) {
-        for (int i = 0; i < 2; i++)
-            if (ctx->wave_events[i][g]) cudaEventDestroy(ctx->wave_events[i][g]);
-        if (ctx->wave_streams[g]) cudaStreamDestroy(ctx->wave_streams[g]);
-    }
-    if (ctx->wave_fork) cudaEventDestroy(ctx->wave_fork);
+    cudaFree(ctx->wave_staging);
+    for (int i = 0; i < 2; i++)
+        if (ctx->wave_events[i]) cudaEventDestroy(ctx->wave_events[i]);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1335,6 +1321,19 @@ int rt_tonemap_rgb8(RtContext* ctx, uint32_t sample_total, uint8_t* rgb8_out) {
     return RT_OK;
 }
 
+int rt_set_profiling(RtContext* ctx, int enabled) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    ctx->profiling = enabled != 0;
+    memset(&ctx->profile, 0, sizeof ctx->profile);
+    return RT_OK;
+}
+
+int rt_get_profile(RtContext* ctx, RtWaveProfile* out) {
+    if (!ctx || !out) return RT_ERR_INVALID_ARGUMENT;
+    *out = ctx->profile;
+    return RT_OK;
+}
+
 int rt_set_detailed_counters(RtContext* ctx, int enabled) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     ctx->detailed = enabled != 0;
@@ -1490,13 +1489,20 @@ int rt_group_render(RtGroup* g, uint32_t sample_begin, uint32_t sample_count, ui
                     uint32_t env_index) {
     if (!g) return RT_ERR_INVALID_ARGUMENT;
     uint32_t n = (uint32_t)g->ctxs.size();
+    // rt_render paces its waves from the calling thread, so every device gets its own.
+    std::vector<int> status(n, RT_OK);
+    std::vector<std::thread> workers;
     for (uint32_t r = 0; r < n; r++) {
         // Contiguous, disjoint sample ranges whose union is the single-GPU range.
         uint32_t lo = (uint32_t)((uint64_t)sample_count * r / n);
         uint32_t hi = (uint32_t)((uint64_t)sample_count * (r + 1) / n);
-        int st = rt_render(g->ctxs[r], sample_begin + lo, hi - lo, max_bounces, env_index);
-        if (st != RT_OK) return st;
+        workers.emplace_back([=, &status] {
+            status[r] = rt_render(g->ctxs[r], sample_begin + lo, hi - lo, max_bounces, env_index);
+        });
     }
+    for (auto& w : workers) w.join();
+    for (uint32_t r = 0; r < n; r++)
+        if (status[r] != RT_OK) return status[r];
     return RT_OK;
 }
 

@@ -19,10 +19,13 @@
 // The bounce ray and the shadow ray of one hit do not depend on each other and travel in
 // the same wave. Path state lives in global memory (~170 B per slot).
 //
-// A slot owns one pixel for all of that pixel's samples and traces them in sample order,
-// then moves to its next pixel (slot + k * slot_count in an 8x8-tile-major numbering), so
-// the accumulation order — and with it every bit of the result — is the reference's
-// frame-by-frame order (shader.wgsl:1367-1371) regardless of scheduling.
+// Paths are independent work items: a slot that finishes a path takes the next path index
+// from a global counter (sample-major, pixels in 8x8-tile order inside a sample), so the
+// slot population stays full until the work runs out. To keep every bit of the result, the
+// radiance of sample k of a pixel is parked in a staging plane and `wave_accumulate_kernel`
+// adds the planes to the accumulation buffer in sample order at the end of a batch — the
+// reference's frame-by-frame order (shader.wgsl:1367-1371) — whatever order the paths
+// finished in.
 #pragma once
 
 #include "rt_fast.cuh"
@@ -62,8 +65,9 @@ enum SlotStage : uint8_t {
 struct WaveCtrl {
     uint32_t ray_n[2];
     uint32_t ray_head[2];
-    uint32_t live;  // slots not yet retired
-    uint32_t pad[3];
+    uint32_t live;       // slots not yet retired
+    uint32_t next_path;  // next path index of the batch to hand out
+    uint32_t pad[2];
 };
 
 struct WaveBuffers {
@@ -93,10 +97,10 @@ struct WaveParams {
     unsigned long long* counters;
     uint32_t width, height;
     uint32_t tiles_x, pixel_ids;  // 8x8-tile-major pixel numbering (ids of partial tiles included)
-    uint32_t slots;        // slots of this group (buffers are indexed 0 .. slots-1)
-    uint32_t slot_base;    // first pixel id of this group's slot 0
-    uint32_t slot_stride;  // pixel ids between a slot's consecutive pixels = slots of all groups
-    uint32_t sample_begin, sample_count;
+    float4* staging;       // [batch_count][width * height] radiance of each finished sample
+    uint32_t slots;
+    uint32_t batch_begin, batch_count;  // the samples of this batch
+    uint32_t path_total;   // batch_count * pixel_ids path indices (ids of partial tiles are skipped)
     uint32_t max_bounces;
     uint32_t wave;
 };
@@ -108,14 +112,6 @@ RT_DEVONLY bool pixel_of_id(const WaveParams& p, uint32_t id, uint32_t& px, uint
     return px < p.width && py < p.height;
 }
 
-// First valid pixel id at or after `id` in this slot's sequence, or kNone.
-RT_DEVONLY uint32_t next_pixel_id(const WaveParams& p, uint32_t id, uint32_t& px, uint32_t& py) {
-    while (id < p.pixel_ids) {
-        if (pixel_of_id(p, id, px, py)) return id;
-        id += p.slot_stride;
-    }
-    return kNone;
-}
 
 // Appends one entry per requesting lane with a single atomic per warp. Every lane of the
 // warp must call it.
@@ -155,13 +151,14 @@ RT_DEVONLY void sts(T* ptr, T v) {
 __global__ void wave_init_kernel(const WaveParams p) {
     uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot < p.slots) {
-        sts(&p.b.pI[slot], make_uint4(p.slot_base + slot, p.sample_begin, 0u, SLOT_NEW));
+        sts(&p.b.pI[slot], make_uint4(0u, 0u, 0u, SLOT_NEW));
         p.b.stage[slot] = STAGE_FINISH;  // every slot starts its first path in wave 0's finish pass
     }
     if (slot == 0) {
         WaveCtrl c;
         memset(&c, 0, sizeof c);
         c.live = p.slots;
+        c.next_path = 0u;
         *p.b.ctrl = c;
     }
 }
@@ -292,21 +289,22 @@ __global__ void __launch_bounds__(kShadeThreads, RT_WAVE_SHADE_MIN_BLOCKS) wave_
 #define RT_WAVE_FINISH_MIN_BLOCKS 8
 #endif
 
-// Slots whose ray escaped (sky light), whose path ended, or that are new: accumulate the
-// finished sample and start the pixel's next one.
+// Slots whose ray escaped (sky light), whose path ended, or that are new: park the finished
+// sample and start the next path of the batch.
 __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wave_finish_kernel(const WaveParams p) {
     const uint32_t P = p.wave & 1u;
     WaveCtrl* c = p.b.ctrl;
     uint32_t* rayq = p.b.rayq + (size_t)P * 2u * p.slots;
     const float sin_half_fov = rt_sin(p.camera.fov_y / 2.0f);
-    const uint32_t sample_end = p.sample_begin + p.sample_count;
+    const size_t pixels = (size_t)p.width * p.height;
     uint32_t n_paths = 0, n_rays = 0;
     sweep_stage<kFinishThreads>(p, STAGE_FINISH, STAGE_FINISH_NEXT, STAGE_FINISH, [&](uint32_t slot, bool on) {
         bool emit = false, retire = false;
+        uint4 I = make_uint4(0u, 0u, 0u, SLOT_RETIRED);
+        PathRegs s;
+        s.rng = 0u;
         if (on) {
-            uint4 I = lds(&p.b.pI[slot]);
-            PathRegs s;
-            uint32_t px = 0, py = 0;
+            I = lds(&p.b.pI[slot]);
             if (I.w != SLOT_NEW) {
                 load_path(p, slot, s);
                 settle_shadow(p, slot, s);
@@ -320,27 +318,34 @@ __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wav
                     float w = power_heuristic(s.last_pdf, pdf);
                     s.L = s.L + s.T * sky * w;
                 }
-                // shader.wgsl:1367-1371: total += sample, alpha = 1. Only this slot touches the pixel.
-                pixel_of_id(p, I.x, px, py);
-                float4* a = p.accum + (size_t)py * p.width + px;
-                float4 v = *a;
-                v.x = v.x + s.L.x;
-                v.y = v.y + s.L.y;
-                v.z = v.z + s.L.z;
-                v.w = 1.0f;
-                *a = v;
-                I.y++;
-                if (I.y >= sample_end) {
-                    I.x += p.slot_stride;  // this pixel is complete: on to the slot's next one
-                    I.y = p.sample_begin;
-                }
+                // Park the sample; wave_accumulate_kernel adds the planes in sample order.
+                p.staging[(size_t)(I.y - p.batch_begin) * pixels + I.x] = make_float4(s.L.x, s.L.y, s.L.z, 0.0f);
             }
-            I.x = next_pixel_id(p, I.x, px, py);
-            if (I.x == kNone) {
+        }
+        // ---- hand out the next path indices: one atomic per warp ----
+        uint32_t q = kNone;
+        {
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, on);
+            if (m) {
+                const uint32_t lane = threadIdx.x & 31u;
+                const int leader = __ffs(m) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(&c->next_path, (uint32_t)__popc(m));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (on) q = base + __popc(m & ((1u << lane) - 1u));
+            }
+        }
+        if (on) {
+            uint32_t px = 0, py = 0;
+            // ids of partial tiles name no pixel: draw again (only for sizes not divisible by 8)
+            while (q < p.path_total && !pixel_of_id(p, q % p.pixel_ids, px, py)) q = atomicAdd(&c->next_path, 1u);
+            if (q >= p.path_total) {
                 I.w = SLOT_RETIRED;
                 p.b.stage[slot] = STAGE_IDLE;
                 retire = true;
             } else {
+                I.x = py * p.width + px;
+                I.y = p.batch_begin + q / p.pixel_ids;
                 V3 o, d;
                 camera_ray(p.camera, sin_half_fov, px, py, p.width, p.height, I.y, s.rng, o, d);
                 s.T = v3s(1.f);
@@ -365,6 +370,23 @@ __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wav
         if (gone && (threadIdx.x & 31u) == 0u) atomicSub(&c->live, (uint32_t)__popc(gone));
     });
     fast_flush_counts(n_paths, n_rays, 0u, p.counters);
+}
+
+// End of a batch: add the staged sample planes to the accumulation buffer in sample order
+// (shader.wgsl:1367-1371: total += sample, alpha = 1).
+__global__ void wave_accumulate_kernel(const WaveParams p) {
+    const size_t pixels = (size_t)p.width * p.height;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pixels) return;
+    float4 a = p.accum[i];
+    for (uint32_t k = 0; k < p.batch_count; k++) {
+        const float4 v = __ldcs(&p.staging[(size_t)k * pixels + i]);
+        a.x = a.x + v.x;
+        a.y = a.y + v.y;
+        a.z = a.z + v.z;
+    }
+    a.w = 1.0f;
+    p.accum[i] = a;
 }
 
 #ifndef RT_WAVE_PREPASS_MIN_BLOCKS
