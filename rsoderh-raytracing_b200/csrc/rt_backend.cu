@@ -380,7 +380,8 @@ struct RtContext {
     struct Env {
         cudaArray_t array = nullptr;
         cudaTextureObject_t texture = 0;
-        float4* d_alias = nullptr;
+        float4* d_alias = nullptr;   // one allocation: alias table, then the texels in linear memory
+        float4* d_texels = nullptr;
         uint32_t width = 0, height = 0;
     };
     std::vector<Env> envs;
@@ -563,6 +564,7 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
     p.scene = ctx->fast;
     p.env.texture = e.texture;
     p.env.alias = e.d_alias;
+    p.env.texels = e.d_texels;
     p.env.width = e.width;
     p.env.height = e.height;
     p.camera = ctx->camera;
@@ -1048,9 +1050,11 @@ int rt_upload_environments(RtContext* ctx, const RtEnvironmentDesc* envs, uint32
         tex.readMode = cudaReadModeElementType;
         tex.normalizedCoords = 0;
         RT_CUDA(ctx, cudaCreateTextureObject(&e.texture, &res, &tex, nullptr));
-        RT_CUDA(ctx, cudaMalloc(&e.d_alias, texels * sizeof(float4)));
+        RT_CUDA(ctx, cudaMalloc(&e.d_alias, 2 * texels * sizeof(float4)));
+        e.d_texels = e.d_alias + texels;
         RT_CUDA(ctx, cudaMemcpy(e.d_alias, envs[i].alias, texels * sizeof(RtAliasEntry),
                                 cudaMemcpyHostToDevice));
+        RT_CUDA(ctx, cudaMemcpy(e.d_texels, envs[i].rgba, texels * sizeof(float4), cudaMemcpyHostToDevice));
         ctx->envs.push_back(e);
     }
     return RT_OK;
@@ -1139,6 +1143,8 @@ int rt_render(RtContext* ctx, uint32_t sample_begin, uint32_t sample_count, uint
         p.scene = ctx->fast;
         p.env.texture = e.texture;
         p.env.alias = e.d_alias;
+        p.env.texels = e.d_texels;
+    p.env.texels = e.d_texels;
         p.env.width = e.width;
         p.env.height = e.height;
         p.camera = ctx->camera;
@@ -1160,6 +1166,8 @@ int rt_render(RtContext* ctx, uint32_t sample_begin, uint32_t sample_count, uint
         p.scene = ctx->scene;
         p.env.texture = e.texture;
         p.env.alias = e.d_alias;
+        p.env.texels = e.d_texels;
+    p.env.texels = e.d_texels;
         p.env.width = e.width;
         p.env.height = e.height;
         p.camera = ctx->camera;
@@ -1193,6 +1201,8 @@ int rt_render(RtContext* ctx, uint32_t sample_begin, uint32_t sample_count, uint
         p.scene = ctx->scene;
         p.env.texture = e.texture;
         p.env.alias = e.d_alias;
+        p.env.texels = e.d_texels;
+    p.env.texels = e.d_texels;
         p.env.width = e.width;
         p.env.height = e.height;
         p.camera = ctx->camera;

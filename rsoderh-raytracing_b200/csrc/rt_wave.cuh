@@ -148,6 +148,22 @@ RT_DEVONLY void sts(T* ptr, T v) {
 #endif
 }
 
+// Two optional entries per lane (a and b) with ONE atomic per warp: the a entries first, then
+// the b entries. Every lane of the warp must call it.
+RT_DEVONLY void list_push2(uint32_t* list, uint32_t* count, bool want_a, uint32_t entry_a, bool want_b,
+                           uint32_t entry_b) {
+    const unsigned ma = __ballot_sync(0xFFFFFFFFu, want_a), mb = __ballot_sync(0xFFFFFFFFu, want_b);
+    if (!(ma | mb)) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t na = (uint32_t)__popc(ma);
+    uint32_t base = 0;
+    if (lane == 0u) base = atomicAdd(count, na + (uint32_t)__popc(mb));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (want_a) list[base + __popc(ma & below)] = entry_a;
+    if (want_b) list[base + na + __popc(mb & below)] = entry_b;
+}
+
 __global__ void wave_init_kernel(const WaveParams p) {
     uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot < p.slots) {
@@ -279,8 +295,7 @@ __global__ void __launch_bounds__(kShadeThreads, RT_WAVE_SHADE_MIN_BLOCKS) wave_
             sts(&p.b.pI[slot], I);
             store_path(p, slot, s);
         }
-        list_push(rayq, &c->ray_n[P], emit_closest, slot);
-        list_push(rayq, &c->ray_n[P], emit_shadow, slot | kShadowBit);
+        list_push2(rayq, &c->ray_n[P], emit_closest, slot, emit_shadow, slot | kShadowBit);
     });
     fast_flush_counts(0u, n_rays, n_shadow, p.counters);
 }
