@@ -23,7 +23,6 @@
 
 #include "rt_backend.h"
 #include "rt_device.cuh"
-#include "rt_pool.cuh"
 #include "rt_fast.cuh"
 #include "rt_fast_host.hpp"
 #include "rt_wave.cuh"
@@ -394,10 +393,8 @@ struct RtContext {
     float4* d_accum = nullptr;
 
     unsigned long long* d_counters = nullptr;
-    uint32_t* d_next_pixel = nullptr;
-    uint32_t* d_stack_scratch = nullptr;  // only for BVHs deeper than the shared-memory stacks
     int sm_count = 0;
-    enum Kernel { KERNEL_WAVE, KERNEL_FAST, KERNEL_PIXEL, KERNEL_POOL };
+    enum Kernel { KERNEL_WAVE, KERNEL_FAST, KERNEL_PIXEL };
     Kernel kernel = KERNEL_WAVE;
     // wavefront pipeline state (rt_wave.cuh)
     rtw::WaveBuffers wave{};
@@ -411,7 +408,6 @@ struct RtContext {
     cudaEvent_t wave_events[2] = {nullptr, nullptr};
     bool profiling = false;
     RtWaveProfile profile{};
-    bool pool_launched = false;
     bool detailed = false;
     uint64_t launches = 0;
 };
@@ -726,18 +722,6 @@ cudaError_t launch_first_hit(const FirstHitParams& p, uint32_t depth, cudaStream
     return cudaGetLastError();
 }
 
-// After a synchronisation point: did the pool kernel's watchdog trip?
-int check_pool_status(RtContext* ctx) {
-    if (!ctx->pool_launched) return RT_OK;
-    uint32_t words[8] = {0};
-    cudaError_t e = cudaMemcpy(words, ctx->d_next_pixel, sizeof words, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
-    if (words[1] != 0u)
-        return fail(ctx, RT_ERR_CUDA, "render kernel watchdog tripped (code 0x%x: %u %u %u)", words[1],
-                    words[2], words[3], words[4]);
-    return RT_OK;
-}
-
 int check_ready(RtContext* ctx, uint32_t env_index, bool need_env) {
     if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "no scene uploaded (rt_upload_scene)");
     if (!ctx->has_camera) return fail(ctx, RT_ERR_STATE, "no camera set (rt_set_camera)");
@@ -793,20 +777,12 @@ int rt_create(int device, RtContext** out) {
         return bail("cudaMalloc(counters)", e);
     if ((e = cudaMemset(ctx->d_counters, 0, sizeof(RtCounters))) != cudaSuccess)
         return bail("cudaMemset(counters)", e);
-    if ((e = cudaMalloc(&ctx->d_next_pixel, 8 * sizeof(uint32_t))) != cudaSuccess)
-        return bail("cudaMalloc(work counter)", e);
     if ((e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
         return bail("cudaDeviceGetAttribute", e);
-    if ((e = cudaFuncSetAttribute(rtp::render_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)rtp::pool_smem_bytes())) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(rtp::render_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)rtp::pool_smem_bytes())) != cudaSuccess)
-        return bail("cudaFuncSetAttribute(shared memory)", e);
     if (const char* k = getenv("RT_KERNEL")) {
         // Development switch: the reference-order kernels are kept for the detailed work counters.
         if (!strcmp(k, "pixel")) ctx->kernel = RtContext::KERNEL_PIXEL;
         else if (!strcmp(k, "fast")) ctx->kernel = RtContext::KERNEL_FAST;
-        else if (!strcmp(k, "pool")) ctx->kernel = RtContext::KERNEL_POOL;
     }
     if (const char* k = getenv("RT_WAVE_SLOTS")) {
         long v = atol(k);
@@ -833,8 +809,6 @@ void rt_destroy(RtContext* ctx) {
     free_envs(ctx);
     cudaFree(ctx->d_accum_own);
     cudaFree(ctx->d_counters);
-    cudaFree(ctx->d_next_pixel);
-    cudaFree(ctx->d_stack_scratch);
     cudaFree(ctx->wave_arena);
     if (ctx->wave_live_host) cudaFreeHost(ctx->wave_live_host);
     cudaFree(ctx->wave_staging);
@@ -1011,11 +985,6 @@ int rt_upload_scene(RtContext* ctx, const RtSceneDesc* s) {
     ctx->node_count = s->bvh_node_count;
     ctx->record_count = (uint32_t)rec_count;
     ctx->material_count = s->material_count;
-    cudaFree(ctx->d_stack_scratch);
-    ctx->d_stack_scratch = nullptr;
-    if (depth > rtp::kSmemStack)
-        RT_CUDA(ctx, cudaMalloc(&ctx->d_stack_scratch,
-                                (size_t)ctx->sm_count * rtp::kSlots * rtp::kGlobalStack * sizeof(uint32_t)));
     ctx->has_scene = true;
     return RT_OK;
 }
@@ -1161,41 +1130,6 @@ int rt_render(RtContext* ctx, uint32_t sample_begin, uint32_t sample_count, uint
         dim3 grid((p.width + rtf::kFastTileW - 1) / rtf::kFastTileW, (p.height + rtf::kFastTileH - 1) / rtf::kFastTileH);
         rtf::render_fast_kernel<<<grid, rtf::kFastThreads, 0, ctx->stream>>>(p);
         e2 = cudaGetLastError();
-    } else if (ctx->kernel == RtContext::KERNEL_POOL) {
-        rtp::PoolParams p;
-        p.scene = ctx->scene;
-        p.env.texture = e.texture;
-        p.env.alias = e.d_alias;
-        p.env.texels = e.d_texels;
-    p.env.texels = e.d_texels;
-        p.env.width = e.width;
-        p.env.height = e.height;
-        p.camera = ctx->camera;
-        p.accum = ctx->d_accum;
-        p.counters = ctx->d_counters;
-        p.next_pixel = ctx->d_next_pixel;
-        p.stack_scratch = ctx->d_stack_scratch;
-        p.width = ctx->width;
-        p.height = ctx->height;
-        p.tiles_x = (ctx->width + 7u) / 8u;
-        p.pixel_ids = p.tiles_x * ((ctx->height + 7u) / 8u) * 64u;
-        p.sample_begin = sample_begin;
-        p.sample_count = sample_count;
-        p.max_bounces = max_bounces;
-        p.node_count = ctx->node_count;
-        p.record_count = ctx->record_count;
-        p.material_count = ctx->material_count;
-        RT_CUDA(ctx, cudaMemsetAsync(ctx->d_next_pixel, 0, 8 * sizeof(uint32_t), ctx->stream));
-        ctx->pool_launched = true;
-        // One persistent block per SM; fewer when the frame has fewer pixels than slots.
-        uint32_t pixels = ctx->width * ctx->height;
-        uint32_t blocks = (pixels + rtp::kSlots - 1) / rtp::kSlots;
-        if (blocks > (uint32_t)ctx->sm_count) blocks = (uint32_t)ctx->sm_count;
-        if (ctx->detailed)
-            rtp::render_pool_kernel<true><<<blocks, rtp::kThreads, rtp::pool_smem_bytes(), ctx->stream>>>(p);
-        else
-            rtp::render_pool_kernel<false><<<blocks, rtp::kThreads, rtp::pool_smem_bytes(), ctx->stream>>>(p);
-        e2 = cudaGetLastError();
     } else {
         RenderParams p;
         p.scene = ctx->scene;
@@ -1283,7 +1217,7 @@ int rt_sync(RtContext* ctx) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return check_pool_status(ctx);
+    return RT_OK;
 }
 
 int rt_read_accum(RtContext* ctx, float* rgba_out) {
@@ -1295,7 +1229,7 @@ int rt_read_accum(RtContext* ctx, float* rgba_out) {
                                  (size_t)ctx->width * ctx->height * sizeof(float4),
                                  cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return check_pool_status(ctx);
+    return RT_OK;
 }
 
 int rt_write_accum(RtContext* ctx, const float* rgba_in) {

@@ -1,0 +1,136 @@
+"""GPU tests of the wavefront pipeline (rt_wave.cuh) and the fast traversal (rt_fast.cuh):
+bit-exact against the oracle and against the backend's other kernels, on the cases the
+shipped scenes do not reach — tiny slot pools and several staging batches, frame sizes
+with partial 8x8 tiles, exact ties across leaves, scenes whose analytic primitives are
+not hoisted (with a plane that sticks out of its leaf box), a deep triangle-only tree.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ASSETS
+from test_fast_emu import _cube_at
+
+pytestmark = pytest.mark.gpu
+
+
+def _render(rt, scene, env, w, h, spp, bounces, begin=0, **kw):
+    st = rt.State(scene, env, w, h, device=0, max_bounces=bounces, **kw)
+    st.reset_counters()
+    st.render_range(begin, spp)
+    return st, st.read_accum()
+
+
+def _report(a, b):
+    bad = np.argwhere((a != b).any(axis=-1))
+    return f"{len(bad)} pixels differ, first {bad[:4].tolist()}"
+
+
+def test_all_kernels_agree_bit_for_bit(rt, house, env_small, monkeypatch):
+    w, h = 200, 112
+    images = {}
+    for kernel in ("wave", "fast", "pixel"):
+        monkeypatch.setenv("RT_KERNEL", kernel)
+        st, images[kernel] = _render(rt, house, env_small, w, h, 3, 8)
+        c = st.counters()
+        assert c["paths"] == w * h * 3
+        images[kernel + "_counts"] = (c["paths"], c["rays"], c["shadow_rays"])
+    assert images["wave"].tobytes() == images["fast"].tobytes() == images["pixel"].tobytes()
+    assert images["wave_counts"] == images["fast_counts"] == images["pixel_counts"]
+
+
+@pytest.mark.parametrize("slots,staging_mb,w,h,spp", [(1024, 1, 203, 117, 5), (4096, 1, 320, 180, 9),
+                                                     (1 << 20, 2048, 161, 90, 4)])
+def test_slot_pool_and_batches(rt, orc, house, env_small, monkeypatch, slots, staging_mb, w, h, spp):
+    # Few slots: every slot traces many paths; a 1 MB staging budget: several batches
+    # (1 MB / (w*h*16 B) samples each); sizes with partial 8x8 tiles: skipped path indices.
+    monkeypatch.setenv("RT_WAVE_SLOTS", str(slots))
+    monkeypatch.setenv("RT_WAVE_STAGING_MB", str(staging_mb))
+    st, got = _render(rt, house, env_small, w, h, spp, 8, begin=3)
+    want, counters = orc.Oracle(house, env_small, w, h, max_bounces=8).render(3, spp)
+    assert got.tobytes() == want.tobytes(), _report(got, want)
+    c = st.counters()
+    assert (c["paths"], c["rays"], c["shadow_rays"]) == (counters["paths"], counters["rays"],
+                                                         counters["shadow_rays"])
+    assert (got[..., 3] == 1.0).all()
+
+
+def test_progressive_calls_equal_one_call(rt, house, env_small):
+    w, h = 128, 72
+    st, one = _render(rt, house, env_small, w, h, 7, 8)
+    st.reset()
+    for k in range(7):
+        st.render_range(k, 1)
+    assert st.read_accum().tobytes() == one.tobytes()
+
+
+def test_ties_and_duplicates_scene(rt, orc, env_small):
+    b = rt.SceneBuilder().add_material((0.8, 0.8, 0.8), 1.0, 0.0).add_material((0.9, 0.6, 0.3), 0.2, 1.0)
+    for _ in range(3):
+        b.add_plane((-4, -1, -4), (0, 0, 8), (8, 0, 0), 0)
+    b.add_plane((-1, 1, -1), (0, 0, 2), (2, 0, 0), 1)      # on the cube's top face
+    b.add_sphere((3, 0, 0), 1.0, 1).add_sphere((3, 0, 0), 1.0, 0)
+    b.add_sphere((0, 0, 3), 0.5, 0)
+    b.add_mesh_obj(_cube_at((0, 0, 0)), 0).add_mesh_obj(_cube_at((0, 0, 0)), 1)
+    b.add_mesh_obj(_cube_at((-3, 0, 0), 0.5), 0)
+    scene = b.set_camera((0.5, 1.5, 6), 0.0, -0.15, 1.2).build()
+    w, h = 192, 108
+    st, got = _render(rt, scene, env_small, w, h, 3, 6)
+    ora = orc.Oracle(scene, env_small, w, h, max_bounces=6)
+    want, _ = ora.render(0, 3)
+    assert got.tobytes() == want.tobytes(), _report(got, want)
+    slots, t = st.first_hit(0)
+    oslots, ot, _ = ora.first_hit(0)
+    assert np.array_equal(slots, oslots) and t.tobytes() == ot.tobytes()
+
+
+def test_many_analytic_primitives_not_hoisted(rt, orc, env_small):
+    # 46 spheres / planes: more than the pre-pass takes, so they stay in the BVH leaves; the
+    # random planes are skewed parallelograms that stick out of their leaf boxes
+    # (scene.rs:203-207 bounds two corners only), so the walk must not prune.
+    rng = np.random.default_rng(5)
+    b = rt.SceneBuilder().add_material((0.8, 0.8, 0.8), 1.0, 0.0).add_material((0.7, 0.7, 0.9), 0.1, 1.0)
+    for _ in range(40):
+        b.add_sphere(tuple(rng.uniform(-4, 4, 3)), float(rng.uniform(0.2, 0.8)), int(rng.integers(0, 2)))
+    for _ in range(6):
+        b.add_plane(tuple(rng.uniform(-4, 4, 3)), tuple(rng.uniform(-2, 2, 3)), tuple(rng.uniform(-2, 2, 3)), 0)
+    b.add_mesh_obj(_cube_at((0, 0, 0)), 0)
+    scene = b.set_camera((0, 1, 9), 0.0, 0.0, 1.2).build()
+    w, h = 160, 90
+    st, got = _render(rt, scene, env_small, w, h, 2, 5)
+    ora = orc.Oracle(scene, env_small, w, h, max_bounces=5)
+    want, _ = ora.render(0, 2)
+    assert got.tobytes() == want.tobytes(), _report(got, want)
+    slots, t = st.first_hit(0)
+    oslots, ot, _ = ora.first_hit(0)
+    assert np.array_equal(slots, oslots) and t.tobytes() == ot.tobytes()
+
+
+def test_synthetic_field_deep_tree(rt, orc, env_small):
+    # The config-D generator at a small grid: ~9k triangles over one ground plane.
+    scene = rt.Scene.synthetic_field(ASSETS, 3)
+    assert scene.counts()["triangles"] > 5000
+    w, h = 256, 144
+    st, got = _render(rt, scene, env_small, w, h, 1, 4)
+    ora = orc.Oracle(scene, env_small, w, h, max_bounces=4)
+    want, _ = ora.render(0, 1)
+    assert got.tobytes() == want.tobytes(), _report(got, want)
+    slots, t = st.first_hit(0)
+    oslots, ot, _ = ora.first_hit(0)
+    assert np.array_equal(slots, oslots) and t.tobytes() == ot.tobytes()
+    assert (slots != 0xFFFFFFFF).mean() > 0.3
+
+
+def test_profile_reports_every_kernel(rt, house, env_small):
+    st = rt.State(house, env_small, 256, 144, device=0, max_bounces=8)
+    st.set_profiling(True)
+    st.render_samples(4)
+    st.sync()
+    prof = st.profile()
+    st.set_profiling(False)
+    assert prof["renders"] == 1 and prof["waves"] >= 8
+    for name, k in prof["kernels"].items():
+        assert k["launches"] == prof["waves"] and k["ms"] > 0, name
+    assert sum(k["ms"] for k in prof["kernels"].values()) <= prof["total_ms"] * 1.05
+    assert st.launch_count() >= 4 * prof["waves"]
