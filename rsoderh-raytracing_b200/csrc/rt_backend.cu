@@ -370,6 +370,7 @@ struct RtContext {
     float4* d_ana = nullptr;
     float4* d_pre = nullptr;
     uint32_t* d_big_len = nullptr;
+    uint32_t* d_ana_paths = nullptr;
     rtf::FastScene fast{};
     uint32_t bvh_depth = 0;
     uint32_t node_count = 0, record_count = 0, material_count = 0;
@@ -403,7 +404,7 @@ struct RtContext {
     uint32_t wave_max_slots = 8192u * 1024u;
     void* wave_staging = nullptr;     // per-sample radiance planes of the current batch
     size_t wave_staging_bytes = 0;
-    size_t wave_staging_budget = (size_t)2048 << 20;
+    size_t wave_staging_budget = (size_t)8192 << 20;
     uint32_t* wave_live_host = nullptr;  // pinned read-back of WaveCtrl::live, one word per chunk in flight
     cudaEvent_t wave_events[2] = {nullptr, nullptr};
     bool profiling = false;
@@ -448,6 +449,8 @@ void free_scene(RtContext* ctx) {
     cudaFree(ctx->d_ana);
     cudaFree(ctx->d_pre);
     cudaFree(ctx->d_big_len);
+    cudaFree(ctx->d_ana_paths);
+    ctx->d_ana_paths = nullptr;
     ctx->d_n2 = ctx->d_tri = ctx->d_ana = ctx->d_pre = nullptr;
     ctx->d_big_len = nullptr;
     ctx->d_nodes = ctx->d_records = ctx->d_tri_normals = ctx->d_materials = nullptr;
@@ -957,12 +960,16 @@ int rt_upload_scene(RtContext* ctx, const RtSceneDesc* s) {
             RT_CUDA(ctx, cudaMemcpy(ctx->d_big_len, fl.big_len.data(), fl.big_len.size() * sizeof(uint32_t),
                                     cudaMemcpyHostToDevice));
         }
+        RT_CUDA(ctx, cudaMalloc(&ctx->d_ana_paths, fl.ana_paths.size() * sizeof(uint32_t)));
+        RT_CUDA(ctx, cudaMemcpy(ctx->d_ana_paths, fl.ana_paths.data(), fl.ana_paths.size() * sizeof(uint32_t),
+                                cudaMemcpyHostToDevice));
         ctx->fast = fl.view;
         ctx->fast.n2 = ctx->d_n2;
         ctx->fast.tri = ctx->d_tri;
         ctx->fast.ana = ctx->d_ana;
         ctx->fast.pre = ctx->d_pre;
         ctx->fast.big_len = ctx->d_big_len;
+        ctx->fast.ana_paths = ctx->d_ana_paths;
     }
     bake_materials_kernel<<<(s->material_count + 127) / 128, 128, 0, ctx->stream>>>(
         d_raw_materials, ctx->d_materials, s->material_count);

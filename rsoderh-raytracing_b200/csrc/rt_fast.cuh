@@ -47,17 +47,28 @@ constexpr uint32_t kPreMaxLeaves = 16, kPreMaxBoxes = 64, kPreMaxPrims = 32;
 constexpr uint32_t kPreMaxFloat4 = kPreMaxLeaves + 2 * kPreMaxBoxes + 4 * kPreMaxPrims;
 
 // Device view of a scene in the fast layout.
-//   n2:   4 x float4 per interior node: (c1.min, ref1) (c1.max, ref2) (c2.min, m) (c2.max, axis)
-//         ref = interior record index, or kLeafBit | len << 26 | first_slot, or kNone for
-//         a child that is never entered (a leaf whose primitives are all hoisted);
-//         m = first slot of the second child's subtree (slots are in DFS order).
+//   n2:   4 x float4 per interior node of the EFFECTIVE tree: (c1.min, ref1) (c1.max, ref2)
+//         (c2.min, -) (c2.max, axis); ref = interior record index or kLeafBit | len << 26 |
+//         first_slot. The effective tree is the reference's tree without the leaves whose
+//         primitives are all hoisted: a node left with one child is spliced out and every
+//         interior box is the union of the LEAF boxes below it (the reference's own leaf
+//         boxes). A leaf box lies inside each of its ancestors' boxes and the slab test is
+//         monotone in the box, so "the leaf's box is hit" already implies that every box
+//         above it is hit: tighter interior boxes only skip work, never a primitive. Leaf
+//         order under a surviving node is the reference's (same split axis), so ties among
+//         triangles resolve by visiting order as before.
 //   tri:  3 x float4 per leaf slot: (a, type) (e0, material) (e1, -); for an analytic slot
 //         the first vector is (bits analytic index, -, -, type).
 //   ana:  4 x float4 per analytic primitive, spheres then planes in reference order:
 //         sphere (pos, 0) (radius, radius^2, bits material, bits slot) (-, -, -, bits index) (-)
 //         plane  (pos, 1) (normal, bits material) (M row x, bits slot) (M row z, bits index)
-//   pre:  the pre-pass program: leaf headers (uint4: box_begin, box_count, prim_begin,
-//         prim_count), then boxes (2 x float4), then primitives (copies of `ana` records).
+//   pre:  the pre-pass program: leaf headers (uint4: box index of the leaf, prim_begin,
+//         prim_count, -), then the distinct boxes on the reference's paths to those leaves,
+//         parents first (2 x float4, min.w = bits parent box index or kNone), then primitives
+//         (copies of `ana` records).
+//   ana_paths: per analytic primitive its root-to-leaf path in the REFERENCE tree, for
+//         precedes(): [analytic_count] offsets, then words m | axis << 28 | side << 30, ended
+//         by kNone (m = first slot of the node's second child, side = which child holds it).
 struct FastScene {
     const float4* __restrict__ n2;
     const float4* __restrict__ tri;
@@ -66,7 +77,8 @@ struct FastScene {
     const float4* __restrict__ materials;
     const uint32_t* __restrict__ big_len;
     const float4* __restrict__ pre;
-    float root_min[3], root_max[3];
+    const uint32_t* __restrict__ ana_paths;
+    float root_min[3], root_max[3];  // box of the effective tree's root
     uint32_t root_ref;
     uint32_t analytic_count;
     uint32_t pre_leaves, pre_boxes, pre_prims;
@@ -124,21 +136,21 @@ RT_DEV uint32_t ana_index(float4 r0, float4 r2, float4 r3) {
     return f_as_i(r0.w) == 0 ? f_as_u(r2.w) : f_as_u(r3.w);
 }
 
-// Does the reference's traversal visit slot a before slot b for a ray with sign mask
-// `neg`? Only consulted when two candidates tie bit for bit. Slots are in DFS order, so
-// at every interior node the first child owns the slots below `m`.
-RT_COLD bool precedes(const float4* __restrict__ n2, uint32_t root_ref, uint32_t a, uint32_t b,
-                                      uint32_t neg) {
-    uint32_t cur = root_ref;
-    while (cur < kLeafBit) {
-        const float4* q = n2 + 4u * (size_t)cur;
-        uint32_t m = f_as_u(ld4(q + 2).w), axis = f_as_u(ld4(q + 3).w);
-        bool a2 = a >= m, b2 = b >= m;
-        if (a2 != b2) return a2 == (((neg >> axis) & 1u) != 0u);
-        cur = a2 ? f_as_u(ld4(q + 1).w) : f_as_u(ld4(q).w);
-        if (cur == kNone) break;  // both in a hoisted leaf
+// Does the reference's traversal visit the analytic primitive `a_index` (in leaf slot
+// a_slot) before slot b for a ray with sign mask `neg`? Only consulted when two candidates
+// tie bit for bit. Slots are in DFS order, so at every node on a's path the first child owns
+// the slots below `m`; the first node that separates the two decides by the sign of 1/d on
+// its split axis (shader.wgsl:536).
+RT_COLD bool precedes(const uint32_t* __restrict__ paths, uint32_t a_index, uint32_t a_slot, uint32_t b_slot,
+                      uint32_t neg) {
+    for (uint32_t i = paths[a_index];; i++) {
+        const uint32_t e = paths[i];
+        if (e == kNone) break;
+        const uint32_t m = e & kLeafSlotMask, axis = (e >> 28) & 3u, side = e >> 30;
+        const uint32_t b_side = b_slot >= m ? 1u : 0u;
+        if (b_side != side) return side == ((neg >> axis) & 1u);
     }
-    return a < b;
+    return a_slot < b_slot;  // same leaf: slot order
 }
 
 RT_DEV uint32_t hit_slot(const FastScene& sc, uint32_t rec) {
@@ -152,8 +164,13 @@ RT_DEV uint32_t hit_slot(const FastScene& sc, uint32_t rec) {
 RT_DEV void offer(const FastScene& sc, const RayCtx& r, FHit& best, float t, uint32_t rec, uint32_t slot,
                   float u, float v, bool in_order) {
     bool take = t < best.t;
-    if (!take && t == best.t && best.rec != kNone && !in_order)
-        take = precedes(sc.n2, sc.root_ref, slot, hit_slot(sc, best.rec), r.neg);
+    if (!take && t == best.t && best.rec != kNone && !in_order) {
+        // one of the two (or both) is a hoisted analytic primitive
+        if (rec & kRecAnalytic)
+            take = precedes(sc.ana_paths, rec & kRecIndexMask, slot, hit_slot(sc, best.rec), r.neg);
+        else
+            take = !precedes(sc.ana_paths, best.rec & kRecIndexMask, hit_slot(sc, best.rec), slot, r.neg);
+    }
     if (take) {
         best.t = t;
         best.rec = rec;
@@ -188,7 +205,7 @@ RT_DEV RayCtx ray_setup(V3 o, V3 d) {
     return r;
 }
 
-// Root box, un-pruned (shader.wgsl:489 for node 0).
+// Box of the effective tree's root, un-pruned.
 RT_DEV bool root_test(const FastScene& sc, const RayCtx& r, float& t0_root) {
     return box_test(r, make_float4(sc.root_min[0], sc.root_min[1], sc.root_min[2], 0.f),
                     make_float4(sc.root_max[0], sc.root_max[1], sc.root_max[2], 0.f), RT_INFINITY, t0_root);
@@ -204,8 +221,8 @@ struct Fallback {
 // ray. `best` receives the closest analytic hit the reference's walk would reach; `fb` the
 // winner of the brute-force loop (spheres, then planes, strict <). `spre` is the block's
 // shared copy of the pre-pass program.
-RT_DEV void prepass(const FastScene& sc, const float4* __restrict__ spre, const RayCtx& r, bool root_ok,
-                    FHit& best, Fallback& fb) {
+RT_DEV void prepass(const FastScene& sc, const float4* __restrict__ spre, const RayCtx& r, FHit& best,
+                    Fallback& fb) {
     best.t = RT_INFINITY;
     best.rec = kNone;
     best.u = 0.0f;
@@ -213,18 +230,21 @@ RT_DEV void prepass(const FastScene& sc, const float4* __restrict__ spre, const 
     fb.t = RT_INFINITY;
     fb.index = kNone;
     if (!sc.hoisted) return;
-    uint32_t best_leaf = kNone;  // pre-pass leaf the current best came from
     const uint32_t box_base = sc.pre_leaves, prim_base = sc.pre_leaves + 2u * sc.pre_boxes;
+    // Which boxes would the reference's (un-pruned) walk get through? Parents come first.
+    unsigned long long reached = 0ull;
+    for (uint32_t b = 0; b < sc.pre_boxes; b++) {
+        const float4 bmin = spre[box_base + 2u * b], bmax = spre[box_base + 2u * b + 1u];
+        const uint32_t parent = f_as_u(bmin.w);
+        float t0;
+        const bool ok = box_test(r, bmin, bmax, RT_INFINITY, t0) && (parent == kNone || ((reached >> parent) & 1ull));
+        reached |= (unsigned long long)ok << b;
+    }
+    uint32_t best_leaf = kNone;  // pre-pass leaf the current best came from
     for (uint32_t l = 0; l < sc.pre_leaves; l++) {
         const float4 hdr = spre[l];
-        const uint32_t b0 = f_as_u(hdr.x), bn = f_as_u(hdr.y);
-        const uint32_t p0 = f_as_u(hdr.z), pn = f_as_u(hdr.w);
-        bool reach = root_ok;  // would the reference's walk arrive at this leaf?
-        for (uint32_t b = 0; b < bn; b++) {
-            float t0;
-            reach = box_test(r, spre[box_base + 2u * (b0 + b)], spre[box_base + 2u * (b0 + b) + 1u],
-                             RT_INFINITY, t0) && reach;
-        }
+        const uint32_t p0 = f_as_u(hdr.y), pn = f_as_u(hdr.z);
+        const bool reach = ((reached >> f_as_u(hdr.x)) & 1ull) != 0ull;
         for (uint32_t k = 0; k < pn; k++) {
             const float4* p = spre + prim_base + 4u * (p0 + k);
             const float4 r0 = p[0], r1 = p[1], r2 = p[2], r3 = p[3];
@@ -309,7 +329,7 @@ RT_DEV bool walk_leaf(const FastScene& sc, const RayCtx& r, bool any_hit, FHit& 
         if (f_as_i(r0.w) == 2) {
             float t = 0.0f, u = 0.0f, v = 0.0f;
             if (test_triangle(r.o, r.d, r0, r1, r2, t, u, v))
-                offer(sc, r, best, t, slot, slot, u, v, best.rec < kRecAnalytic);
+                offer(sc, r, best, t, slot, slot, u, v, !sc.hoisted || best.rec < kRecAnalytic);
         } else if (!sc.hoisted) {
             test_analytic_cold(sc.ana, f_as_u(r0.x), r.o, r.d, best.t, best.rec, kRecAnalytic);
         }
@@ -340,11 +360,11 @@ RT_DEV void resolve_fallback(const FastScene& sc, const RayCtx& r, const Fallbac
 RT_DEV void trace_fast(const FastScene& sc, const float4* __restrict__ spre, V3 o, V3 d, bool any_hit,
                        FHit& best, uint2* stack) {
     const RayCtx r = ray_setup(o, d);
+    Fallback fb;
+    prepass(sc, spre, r, best, fb);
+    if (any_hit && best.rec != kNone) return;
     float t0_root;
     const bool root_ok = root_test(sc, r, t0_root);
-    Fallback fb;
-    prepass(sc, spre, r, root_ok, best, fb);
-    if (any_hit && best.rec != kNone) return;
 
     // the walk ("while-while"): interior records until this lane holds a leaf, then the leaf
     Walk w;

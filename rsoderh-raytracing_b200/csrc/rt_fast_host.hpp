@@ -20,12 +20,6 @@ inline float bits(uint32_t u) {
 
 // ---- fast layout (rt_fast.cuh): N2 interior records, 48-byte triangle records, analytic
 //      records and the pre-pass program. Inputs are already validated. ----
-struct FastLayout {
-    std::vector<float4> n2, tri, ana, pre;
-    std::vector<uint32_t> big_len;
-    FastScene view{};
-};
-
 // Plane::bounds (scene.rs:203-207) is the box of two opposite corners, pos and
 // pos + forward + right. It contains the other two corners iff forward and right never
 // point opposite ways on any axis. forward / right are recovered from the base-change
@@ -64,76 +58,125 @@ inline bool scene_has_loose_plane(const RtSceneDesc& s) {
     return false;
 }
 
+struct FastLayout {
+    std::vector<float4> n2, tri, ana, pre;
+    std::vector<uint32_t> big_len, ana_paths;
+    FastScene view{};
+};
+
 inline void build_fast_layout(const RtSceneDesc& s, FastLayout& out) {
-        const uint32_t nodes = s.bvh_node_count, slots = s.primitive_count;
+    const uint32_t nodes = s.bvh_node_count, slots = s.primitive_count;
     const uint32_t analytic = s.sphere_count + s.plane_count;
 
-    // parents (for the box chains) and interior record numbering in node order
     std::vector<int64_t> parent(nodes, -1);
-    std::vector<uint32_t> record_of(nodes, kNone);
-    uint32_t interior = 0;
     for (uint32_t i = 0; i < nodes; i++) {
         const RtBvhNode& n = s.bvh_nodes[i];
         if (n.primitives_len == 0) {
-            record_of[i] = interior++;
             parent[i + 1] = i;
             parent[n.primitives_or_second_child_index] = i;
         }
     }
-
-    // hoisting decision: few analytic primitives, short chains
-    std::vector<uint32_t> ana_leaves;  // leaves holding at least one analytic primitive, in node (= slot) order
-    uint32_t chain_boxes = 0;
-    for (uint32_t i = 0; i < nodes; i++) {
-        const RtBvhNode& n = s.bvh_nodes[i];
-        if (n.primitives_len == 0) continue;
-        bool any = false;
-        for (uint32_t k = 0; k < n.primitives_len; k++)
-            any |= s.primitives[n.primitives_or_second_child_index + k].primitive_type != 2u;
-        if (!any) continue;
-        ana_leaves.push_back(i);
-        for (int64_t x = i; x > 0; x = parent[x]) chain_boxes++;  // the root is tested once for all
-    }
-    const bool hoisted = analytic <= kPreMaxPrims && ana_leaves.size() <= kPreMaxLeaves &&
-                         chain_boxes <= kPreMaxBoxes;
-
-    auto leaf_all_analytic = [&](const RtBvhNode& n) {
-        for (uint32_t k = 0; k < n.primitives_len; k++)
-            if (s.primitives[n.primitives_or_second_child_index + k].primitive_type == 2u) return false;
-        return true;
-    };
-    bool any_big = false;
-    auto ref_of = [&](uint32_t i) -> uint32_t {
-        const RtBvhNode& n = s.bvh_nodes[i];
-        if (n.primitives_len == 0) return record_of[i];
-        if (hoisted && leaf_all_analytic(n)) return kNone;
-        uint32_t len = n.primitives_len;
-        if (len >= kLeafLenEscape) {
-            any_big = true;
-            len = kLeafLenEscape;
-        }
-        return kLeafBit | (len << kLeafLenShift) | n.primitives_or_second_child_index;
-    };
     auto first_slot_of = [&](uint32_t i) {
         while (s.bvh_nodes[i].primitives_len == 0) i = i + 1;
         return s.bvh_nodes[i].primitives_or_second_child_index;
     };
+    auto leaf_has_analytic = [&](const RtBvhNode& n) {
+        for (uint32_t k = 0; k < n.primitives_len; k++)
+            if (s.primitives[n.primitives_or_second_child_index + k].primitive_type != 2u) return true;
+        return false;
+    };
+    auto leaf_has_triangle = [&](const RtBvhNode& n) {
+        for (uint32_t k = 0; k < n.primitives_len; k++)
+            if (s.primitives[n.primitives_or_second_child_index + k].primitive_type == 2u) return true;
+        return false;
+    };
 
-    out.n2.assign((size_t)interior * 4, make_float4(0.f, 0.f, 0.f, 0.f));
-    for (uint32_t i = 0; i < nodes; i++) {
-        const RtBvhNode& n = s.bvh_nodes[i];
-        if (n.primitives_len != 0) continue;
-        const uint32_t c1 = i + 1, c2 = n.primitives_or_second_child_index;
-        const RtBvhNode &a = s.bvh_nodes[c1], &b = s.bvh_nodes[c2];
-        float4* q = &out.n2[(size_t)record_of[i] * 4];
-        q[0] = make_float4(a.min[0], a.min[1], a.min[2], bits(ref_of(c1)));
-        q[1] = make_float4(a.max[0], a.max[1], a.max[2], bits(ref_of(c2)));
-        q[2] = make_float4(b.min[0], b.min[1], b.min[2], bits(first_slot_of(c2)));
-        q[3] = make_float4(b.max[0], b.max[1], b.max[2], bits(n.split_axis));
+    // ---- hoisting decision: few analytic primitives, few distinct boxes on their paths ----
+    std::vector<uint32_t> ana_leaves;  // leaves holding at least one analytic primitive, in node (= slot) order
+    std::vector<uint32_t> box_nodes;   // distinct reference nodes on the paths to them, parents first
+    {
+        std::vector<char> on_path(nodes, 0);
+        for (uint32_t i = 0; i < nodes; i++) {
+            const RtBvhNode& n = s.bvh_nodes[i];
+            if (n.primitives_len == 0 || !leaf_has_analytic(n)) continue;
+            ana_leaves.push_back(i);
+            for (int64_t x = i; x >= 0; x = parent[x]) on_path[(size_t)x] = 1;
+        }
+        for (uint32_t i = 0; i < nodes && box_nodes.size() <= kPreMaxBoxes; i++)  // node order = parents first
+            if (on_path[i]) box_nodes.push_back(i);
     }
-    if (out.n2.empty()) out.n2.assign(4, make_float4(0.f, 0.f, 0.f, 0.f));  // never read: root is a leaf
+    const bool hoisted = analytic <= kPreMaxPrims && ana_leaves.size() <= kPreMaxLeaves &&
+                         box_nodes.size() <= kPreMaxBoxes;
 
-    // analytic records: spheres then planes, reference order; slots filled in below
+    // ---- the effective tree: interior records over the leaves the walk has to test ----
+    struct Sub {
+        uint32_t ref;  // kNone, leaf ref or interior record index
+        float mn[3], mx[3];
+    };
+    bool any_big = false;
+    std::vector<float4>& n2 = out.n2;
+    n2.clear();
+    // Iterative post-order over the reference tree (depth <= 64, but node counts reach 10^7).
+    std::vector<Sub> result(nodes);
+    {
+        std::vector<uint32_t> order;
+        order.reserve(nodes);
+        std::vector<uint32_t> todo{0u};
+        while (!todo.empty()) {
+            uint32_t i = todo.back();
+            todo.pop_back();
+            order.push_back(i);
+            const RtBvhNode& n = s.bvh_nodes[i];
+            if (n.primitives_len == 0) {
+                todo.push_back(i + 1);
+                todo.push_back(n.primitives_or_second_child_index);
+            }
+        }
+        for (size_t k = order.size(); k-- > 0;) {  // children before parents
+            const uint32_t i = order[k];
+            const RtBvhNode& n = s.bvh_nodes[i];
+            Sub& r = result[i];
+            if (n.primitives_len != 0) {
+                const bool walked = hoisted ? leaf_has_triangle(n) : true;
+                if (!walked) {
+                    r.ref = kNone;
+                    continue;
+                }
+                uint32_t len = n.primitives_len;
+                if (len >= kLeafLenEscape) {
+                    any_big = true;
+                    len = kLeafLenEscape;
+                }
+                r.ref = kLeafBit | (len << kLeafLenShift) | n.primitives_or_second_child_index;
+                for (int a = 0; a < 3; a++) {
+                    r.mn[a] = n.min[a];  // the reference's own leaf box
+                    r.mx[a] = n.max[a];
+                }
+                continue;
+            }
+            const Sub& c1 = result[i + 1];
+            const Sub& c2 = result[n.primitives_or_second_child_index];
+            if (c1.ref == kNone && c2.ref == kNone) {
+                r.ref = kNone;
+            } else if (c1.ref == kNone || c2.ref == kNone) {
+                r = c1.ref == kNone ? c2 : c1;  // spliced out
+            } else {
+                r.ref = (uint32_t)(n2.size() / 4);
+                n2.push_back(make_float4(c1.mn[0], c1.mn[1], c1.mn[2], bits(c1.ref)));
+                n2.push_back(make_float4(c1.mx[0], c1.mx[1], c1.mx[2], bits(c2.ref)));
+                n2.push_back(make_float4(c2.mn[0], c2.mn[1], c2.mn[2], 0.f));
+                n2.push_back(make_float4(c2.mx[0], c2.mx[1], c2.mx[2], bits(n.split_axis)));
+                for (int a = 0; a < 3; a++) {
+                    r.mn[a] = c1.mn[a] < c2.mn[a] ? c1.mn[a] : c2.mn[a];
+                    r.mx[a] = c1.mx[a] > c2.mx[a] ? c1.mx[a] : c2.mx[a];
+                }
+            }
+        }
+    }
+    const Sub root = result[0];
+    if (n2.empty()) n2.assign(4, make_float4(0.f, 0.f, 0.f, 0.f));  // never read: the root is a leaf or empty
+
+    // ---- triangle and analytic records ----
     out.ana.assign((size_t)(analytic ? analytic : 1) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
     std::vector<uint32_t> slot_of_analytic(analytic, kNone);
     out.tri.assign((size_t)slots * 3, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -177,18 +220,29 @@ inline void build_fast_layout(const RtSceneDesc& s, FastLayout& out) {
                 out.big_len[s.bvh_nodes[i].primitives_or_second_child_index] = s.bvh_nodes[i].primitives_len;
     }
 
-    // pre-pass program: headers | boxes | primitive records
+    // ---- pre-pass program: leaf headers | boxes (parents first) | primitive records ----
     uint32_t pre_leaves = 0, pre_boxes = 0, pre_prims = 0;
     std::vector<float4> headers, boxes, prims;
+    out.ana_paths.assign(analytic ? analytic : 1, 0u);
     if (hoisted) {
+        std::vector<uint32_t> box_index(nodes, kNone);
+        for (uint32_t node : box_nodes) {
+            const RtBvhNode& c = s.bvh_nodes[node];
+            const uint32_t par = parent[node] >= 0 ? box_index[(size_t)parent[node]] : kNone;
+            box_index[node] = pre_boxes++;
+            boxes.push_back(make_float4(c.min[0], c.min[1], c.min[2], bits(par)));
+            boxes.push_back(make_float4(c.max[0], c.max[1], c.max[2], 0.f));
+        }
         for (uint32_t leaf : ana_leaves) {
             const RtBvhNode& n = s.bvh_nodes[leaf];
-            const uint32_t b0 = pre_boxes, p0 = pre_prims;
-            for (int64_t x = leaf; x > 0; x = parent[x]) {
-                const RtBvhNode& c = s.bvh_nodes[x];
-                boxes.push_back(make_float4(c.min[0], c.min[1], c.min[2], 0.f));
-                boxes.push_back(make_float4(c.max[0], c.max[1], c.max[2], 0.f));
-                pre_boxes++;
+            const uint32_t p0 = pre_prims;
+            // the leaf's path in the reference tree, root first, for precedes()
+            std::vector<uint32_t> path;
+            for (int64_t x = leaf; parent[x] >= 0; x = parent[x]) {
+                const uint32_t par = (uint32_t)parent[x];
+                const RtBvhNode& pn = s.bvh_nodes[par];
+                const uint32_t side = (uint32_t)x == par + 1u ? 0u : 1u;
+                path.push_back(first_slot_of(pn.primitives_or_second_child_index) | (pn.split_axis << 28) | (side << 30));
             }
             for (uint32_t k = 0; k < n.primitives_len; k++) {
                 const RtPrimitiveInfo& info = s.primitives[n.primitives_or_second_child_index + k];
@@ -196,11 +250,13 @@ inline void build_fast_layout(const RtSceneDesc& s, FastLayout& out) {
                 const uint32_t index = info.primitive_type == 0u ? info.index : s.sphere_count + info.index;
                 for (int j = 0; j < 4; j++) prims.push_back(out.ana[(size_t)index * 4 + j]);
                 pre_prims++;
+                out.ana_paths[index] = (uint32_t)out.ana_paths.size();
+                for (size_t j = path.size(); j-- > 0;) out.ana_paths.push_back(path[j]);
+                out.ana_paths.push_back(kNone);
             }
-            headers.push_back(make_float4(bits(b0), bits(pre_boxes - b0), bits(p0), bits(pre_prims - p0)));
+            headers.push_back(make_float4(bits(box_index[leaf]), bits(p0), bits(pre_prims - p0), 0.f));
             pre_leaves++;
         }
-        // analytic primitives that sit in no leaf cannot exist: every primitive has a slot
     }
     out.pre.clear();
     out.pre.insert(out.pre.end(), headers.begin(), headers.end());
@@ -209,12 +265,11 @@ inline void build_fast_layout(const RtSceneDesc& s, FastLayout& out) {
     if (out.pre.empty()) out.pre.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
 
     FastScene& v = out.view;
-    const RtBvhNode& root = s.bvh_nodes[0];
     for (int k = 0; k < 3; k++) {
-        v.root_min[k] = root.min[k];
-        v.root_max[k] = root.max[k];
+        v.root_min[k] = root.ref == kNone ? 0.f : root.mn[k];
+        v.root_max[k] = root.ref == kNone ? 0.f : root.mx[k];
     }
-    v.root_ref = ref_of(0);
+    v.root_ref = root.ref;
     v.analytic_count = analytic;
     v.pre_leaves = pre_leaves;
     v.pre_boxes = pre_boxes;
@@ -222,6 +277,5 @@ inline void build_fast_layout(const RtSceneDesc& s, FastLayout& out) {
     v.hoisted = hoisted ? 1u : 0u;
     v.no_prune = (!hoisted && scene_has_loose_plane(s)) ? 1u : 0u;
 }
-
 
 }  // namespace rtf

@@ -408,13 +408,15 @@ __global__ void wave_accumulate_kernel(const WaveParams p) {
 #define RT_WAVE_PREPASS_MIN_BLOCKS 4
 #endif
 
-// Ray queue of this wave: the analytic pre-pass, one ray per thread, every lane busy.
+// Ray queue of this wave: the analytic pre-pass, one ray per thread, every lane busy. A ray
+// that the pre-pass settles — a blocked shadow ray, or any ray that misses the box of the
+// effective tree (or enters it beyond the closest analytic hit) — is finished here and
+// leaves the queue; only rays with triangles to test go on to the walk.
 __global__ void __launch_bounds__(kPrepassThreads, RT_WAVE_PREPASS_MIN_BLOCKS) wave_prepass_kernel(const WaveParams p) {
     __shared__ float4 spre[kPreMaxFloat4];
     stage_pre(p.scene, spre);
     const uint32_t P = p.wave & 1u;
     WaveCtrl* c = p.b.ctrl;
-    if (!p.scene.hoisted) return;
     const uint32_t count = c->ray_n[P];
     uint32_t* rayq = p.b.rayq + (size_t)P * 2u * p.slots;
     const uint32_t stride = gridDim.x * kPrepassThreads;
@@ -425,21 +427,26 @@ __global__ void __launch_bounds__(kPrepassThreads, RT_WAVE_PREPASS_MIN_BLOCKS) w
         const V3 o = xyz(lds(&p.b.ray_o[slot]));
         const V3 d = xyz(shadow ? lds(&p.b.sray_d[slot]) : lds(&p.b.ray_d[slot]));
         const RayCtx r = ray_setup(o, d);
-        float t0_root;
-        const bool root_ok = root_test(p.scene, r, t0_root);
         FHit best;
         Fallback fb;
-        prepass(p.scene, spre, r, root_ok, best, fb);
+        prepass(p.scene, spre, r, best, fb);
+        float t0_root;
+        const bool root_ok = root_test(p.scene, r, t0_root);
+        Walk w;
+        walk_begin(p.scene, root_ok, t0_root, best, w);
+        const bool walk = w.cur != kNone && !(shadow && best.rec != kNone);
         if (shadow) {
-            if (best.rec != kNone) {
-                sts(&p.b.occl[slot], 1u);
-                rayq[i] = kDeadEntry;  // settled: the walk skips it
-            }
-        } else {
+            if (best.rec != kNone) sts(&p.b.occl[slot], 1u);
+        } else if (walk) {
             p.b.ray_o[slot].w = best.t;
             p.b.ray_d[slot].w = u_as_f(best.rec);
             sts(&p.b.fb[slot], make_float2(fb.t, u_as_f(fb.index)));
+        } else {
+            resolve_fallback(p.scene, r, fb, best);
+            sts(&p.b.hit[slot], make_float4(best.t, u_as_f(best.rec), best.u, best.v));
+            p.b.stage[slot] = best.rec != kNone ? STAGE_SHADE : STAGE_FINISH;
         }
+        if (!walk) rayq[i] = kDeadEntry;
     }
 }
 
@@ -491,9 +498,7 @@ __global__ void __launch_bounds__(kWalkThreads, RT_WAVE_WALK_MIN_BLOCKS) wave_wa
                     best.t = any_hit ? RT_INFINITY : o4.w;
                     best.rec = any_hit ? kNone : f_as_u(d4.w);
                     best.u = best.v = 0.0f;
-                    float t0_root;
-                    const bool root_ok = root_test(p.scene, r, t0_root);
-                    walk_begin(p.scene, root_ok, t0_root, best, w);
+                    walk_begin(p.scene, true, 0.0f, best, w);  // the pre-pass kernel checked the root box
                     busy = true;
                 }
             }

@@ -37,6 +37,7 @@ void* emu_scene_create(const RtSceneDesc* s) {
     v.tri = e->layout.tri.data();
     v.ana = e->layout.ana.data();
     v.pre = e->layout.pre.data();
+    v.ana_paths = e->layout.ana_paths.data();
     v.big_len = e->layout.big_len.empty() ? nullptr : e->layout.big_len.data();
     v.tri_normals = nullptr;
     v.materials = nullptr;
