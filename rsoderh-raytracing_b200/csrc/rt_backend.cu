@@ -525,14 +525,11 @@ int wave_reserve(RtContext* ctx, uint32_t slots, size_t staging_bytes) {
         RT_CUDA(ctx, cudaMalloc(&ctx->wave_arena, S * (8 * 16 + 8 + 4 + 16 + 1) + 512));
         char* q = (char*)ctx->wave_arena;
         rtw::WaveBuffers& b = ctx->wave;
-        b.ray_o = (float4*)q;  q += S * 16;
-        b.ray_d = (float4*)q;  q += S * 16;
+        b.rOD = (float4*)q;    q += S * 32;
+        b.pTL = (float4*)q;    q += S * 32;
+        b.pPI = (float4*)q;    q += S * 32;
         b.sray_d = (float4*)q; q += S * 16;
         b.hit = (float4*)q;    q += S * 16;
-        b.pT = (float4*)q;     q += S * 16;
-        b.pL = (float4*)q;     q += S * 16;
-        b.pP = (float4*)q;     q += S * 16;
-        b.pI = (uint4*)q;      q += S * 16;
         b.fb = (float2*)q;     q += S * 8;
         b.rayq = (uint32_t*)q; q += S * 16;
         b.occl = (uint32_t*)q; q += S * 4;

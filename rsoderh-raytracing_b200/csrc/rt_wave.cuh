@@ -71,18 +71,17 @@ struct WaveCtrl {
 };
 
 struct WaveBuffers {
-    // Structure of arrays (measured faster than one 128-byte record per slot: the pre-pass and
-    // the walk touch only the ray vectors).
-    float4* ray_o;    // [S] origin of the slot's rays, .w = closest analytic distance from the pre-pass
-    float4* ray_d;    // [S] direction of the closest-hit ray, .w = bits rec of that analytic hit
+    // Arrays of 32-byte pairs: vectors that are always used together share a DRAM sector, so
+    // the scattered slots a warp works on waste no half sectors. (One 128-byte record per
+    // slot measured slower: the pre-pass and the walk touch only the ray vectors.)
+    float4* rOD;      // [S][2] ray origin (.w = closest analytic distance from the pre-pass),
+                      //        direction of the closest-hit ray (.w = bits rec of that analytic hit)
     float4* sray_d;   // [S] direction of the shadow ray
     float2* fb;       // [S] brute-force fallback winner of the closest-hit ray (t, bits index)
     float4* hit;      // [S] (t, bits rec, u, v) written by the walk kernel
     uint32_t* occl;   // [S] 1 when the shadow ray is blocked
-    float4* pT;       // [S] throughput, last_pdf
-    float4* pL;       // [S] radiance of the current sample, bits rng
-    float4* pP;       // [S] pending next-event light, bits flags
-    uint4* pI;        // [S] pixel id, sample, bounce, state
+    float4* pTL;      // [S][2] throughput + last_pdf, radiance of the current sample + bits rng
+    float4* pPI;      // [S][2] pending next-event light + bits flags, bits (pixel, sample, bounce, state)
     uint8_t* stage;   // [S] what the slot needs next (SlotStage)
     uint32_t* rayq;   // [2][2S]
     WaveCtrl* ctrl;
@@ -167,7 +166,7 @@ RT_DEVONLY void list_push2(uint32_t* list, uint32_t* count, bool want_a, uint32_
 __global__ void wave_init_kernel(const WaveParams p) {
     uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot < p.slots) {
-        sts(&p.b.pI[slot], make_uint4(0u, 0u, 0u, SLOT_NEW));
+        sts((uint4*)&p.b.pPI[2u * (size_t)slot + 1u], make_uint4(0u, 0u, 0u, SLOT_NEW));
         p.b.stage[slot] = STAGE_FINISH;  // every slot starts its first path in wave 0's finish pass
     }
     if (slot == 0) {
@@ -186,7 +185,7 @@ struct PathRegs {
 };
 
 RT_DEVONLY void load_path(const WaveParams& p, uint32_t slot, PathRegs& s) {
-    const float4 t4 = lds(&p.b.pT[slot]), l4 = lds(&p.b.pL[slot]), p4 = lds(&p.b.pP[slot]);
+    const float4 t4 = lds(&p.b.pTL[2u * (size_t)slot + 0u]), l4 = lds(&p.b.pTL[2u * (size_t)slot + 1u]), p4 = lds(&p.b.pPI[2u * (size_t)slot + 0u]);
     s.T = xyz(t4);
     s.last_pdf = t4.w;
     s.L = xyz(l4);
@@ -196,9 +195,9 @@ RT_DEVONLY void load_path(const WaveParams& p, uint32_t slot, PathRegs& s) {
 }
 
 RT_DEVONLY void store_path(const WaveParams& p, uint32_t slot, const PathRegs& s) {
-    sts(&p.b.pT[slot], make_float4(s.T.x, s.T.y, s.T.z, s.last_pdf));
-    sts(&p.b.pL[slot], make_float4(s.L.x, s.L.y, s.L.z, u_as_f(s.rng)));
-    sts(&p.b.pP[slot], make_float4(s.pending.x, s.pending.y, s.pending.z, u_as_f(s.flags)));
+    sts(&p.b.pTL[2u * (size_t)slot + 0u], make_float4(s.T.x, s.T.y, s.T.z, s.last_pdf));
+    sts(&p.b.pTL[2u * (size_t)slot + 1u], make_float4(s.L.x, s.L.y, s.L.z, u_as_f(s.rng)));
+    sts(&p.b.pPI[2u * (size_t)slot + 0u], make_float4(s.pending.x, s.pending.y, s.pending.z, u_as_f(s.flags)));
 }
 
 // shader.wgsl:1249-1264: the last next-event sample counts iff nothing blocked its ray.
@@ -260,8 +259,8 @@ __global__ void __launch_bounds__(kShadeThreads, RT_WAVE_SHADE_MIN_BLOCKS) wave_
             PathRegs s;
             load_path(p, slot, s);
             settle_shadow(p, slot, s);
-            uint4 I = lds(&p.b.pI[slot]);
-            const float4 o4 = lds(&p.b.ray_o[slot]), d4 = lds(&p.b.ray_d[slot]), h4 = lds(&p.b.hit[slot]);
+            uint4 I = lds((const uint4*)&p.b.pPI[2u * (size_t)slot + 1u]);
+            const float4 o4 = lds(&p.b.rOD[2u * (size_t)slot + 0u]), d4 = lds(&p.b.rOD[2u * (size_t)slot + 1u]), h4 = lds(&p.b.hit[slot]);
             FHit hit;
             hit.t = h4.x;
             hit.rec = f_as_u(h4.y);
@@ -281,18 +280,18 @@ __global__ void __launch_bounds__(kShadeThreads, RT_WAVE_SHADE_MIN_BLOCKS) wave_
                 n_shadow++;
             }
             // Both rays start at the hit point (no offset: shader.wgsl:1249, 1295).
-            sts(&p.b.ray_o[slot], make_float4(so.point.x, so.point.y, so.point.z, RT_INFINITY));
+            sts(&p.b.rOD[2u * (size_t)slot + 0u], make_float4(so.point.x, so.point.y, so.point.z, RT_INFINITY));
             if (done) {
                 // With a shadow ray in flight the sample is finished one wave later.
                 I.w = emit_shadow ? SLOT_ENDING : SLOT_DONE;
                 p.b.stage[slot] = emit_shadow ? STAGE_FINISH_NEXT : STAGE_FINISH;
             } else {
                 emit_closest = true;
-                sts(&p.b.ray_d[slot], make_float4(so.next_dir.x, so.next_dir.y, so.next_dir.z, u_as_f(kNone)));
+                sts(&p.b.rOD[2u * (size_t)slot + 1u], make_float4(so.next_dir.x, so.next_dir.y, so.next_dir.z, u_as_f(kNone)));
                 p.b.stage[slot] = STAGE_FLIGHT;
                 n_rays++;
             }
-            sts(&p.b.pI[slot], I);
+            sts((uint4*)&p.b.pPI[2u * (size_t)slot + 1u], I);
             store_path(p, slot, s);
         }
         list_push2(rayq, &c->ray_n[P], emit_closest, slot, emit_shadow, slot | kShadowBit);
@@ -319,13 +318,13 @@ __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wav
         PathRegs s;
         s.rng = 0u;
         if (on) {
-            I = lds(&p.b.pI[slot]);
+            I = lds((const uint4*)&p.b.pPI[2u * (size_t)slot + 1u]);
             if (I.w != SLOT_NEW) {
                 load_path(p, slot, s);
                 settle_shadow(p, slot, s);
                 if (I.w == SLOT_TRACED) {
                     // shader.wgsl:1222-1231 — the ray escaped into the environment.
-                    const V3 d = xyz(lds(&p.b.ray_d[slot]));
+                    const V3 d = xyz(lds(&p.b.rOD[2u * (size_t)slot + 1u]));
                     float u, v;
                     direction_to_uv(d, u, v);
                     V3 sky = env_bilinear(p.env, u, v);
@@ -370,15 +369,15 @@ __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wav
                 s.flags = 0u;
                 I.z = 0u;
                 I.w = SLOT_TRACED;
-                sts(&p.b.ray_o[slot], make_float4(o.x, o.y, o.z, RT_INFINITY));
-                sts(&p.b.ray_d[slot], make_float4(d.x, d.y, d.z, u_as_f(kNone)));
+                sts(&p.b.rOD[2u * (size_t)slot + 0u], make_float4(o.x, o.y, o.z, RT_INFINITY));
+                sts(&p.b.rOD[2u * (size_t)slot + 1u], make_float4(d.x, d.y, d.z, u_as_f(kNone)));
                 p.b.stage[slot] = STAGE_FLIGHT;
                 store_path(p, slot, s);
                 emit = true;
                 n_paths++;
                 n_rays++;
             }
-            sts(&p.b.pI[slot], I);
+            sts((uint4*)&p.b.pPI[2u * (size_t)slot + 1u], I);
         }
         list_push(rayq, &c->ray_n[P], emit, slot);
         const unsigned gone = __ballot_sync(0xFFFFFFFFu, retire);
@@ -424,8 +423,8 @@ __global__ void __launch_bounds__(kPrepassThreads, RT_WAVE_PREPASS_MIN_BLOCKS) w
         const uint32_t e = rayq[i];
         const uint32_t slot = e & ~kShadowBit;
         const bool shadow = (e & kShadowBit) != 0u;
-        const V3 o = xyz(lds(&p.b.ray_o[slot]));
-        const V3 d = xyz(shadow ? lds(&p.b.sray_d[slot]) : lds(&p.b.ray_d[slot]));
+        const V3 o = xyz(lds(&p.b.rOD[2u * (size_t)slot + 0u]));
+        const V3 d = xyz(shadow ? lds(&p.b.sray_d[slot]) : lds(&p.b.rOD[2u * (size_t)slot + 1u]));
         const RayCtx r = ray_setup(o, d);
         FHit best;
         Fallback fb;
@@ -438,8 +437,8 @@ __global__ void __launch_bounds__(kPrepassThreads, RT_WAVE_PREPASS_MIN_BLOCKS) w
         if (shadow) {
             if (best.rec != kNone) sts(&p.b.occl[slot], 1u);
         } else if (walk) {
-            p.b.ray_o[slot].w = best.t;
-            p.b.ray_d[slot].w = u_as_f(best.rec);
+            p.b.rOD[2u * (size_t)slot + 0u].w = best.t;
+            p.b.rOD[2u * (size_t)slot + 1u].w = u_as_f(best.rec);
             sts(&p.b.fb[slot], make_float2(fb.t, u_as_f(fb.index)));
         } else {
             resolve_fallback(p.scene, r, fb, best);
@@ -492,8 +491,8 @@ __global__ void __launch_bounds__(kWalkThreads, RT_WAVE_WALK_MIN_BLOCKS) wave_wa
                 if (e != kDeadEntry) {
                     slot = e & ~kShadowBit;
                     any_hit = (e & kShadowBit) != 0u;
-                    const float4 o4 = lds(&p.b.ray_o[slot]);
-                    const float4 d4 = any_hit ? lds(&p.b.sray_d[slot]) : lds(&p.b.ray_d[slot]);
+                    const float4 o4 = lds(&p.b.rOD[2u * (size_t)slot + 0u]);
+                    const float4 d4 = any_hit ? lds(&p.b.sray_d[slot]) : lds(&p.b.rOD[2u * (size_t)slot + 1u]);
                     r = ray_setup(xyz(o4), xyz(d4));
                     best.t = any_hit ? RT_INFINITY : o4.w;
                     best.rec = any_hit ? kNone : f_as_u(d4.w);
