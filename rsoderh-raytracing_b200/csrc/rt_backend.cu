@@ -532,7 +532,7 @@ int wave_reserve(RtContext* ctx, uint32_t slots, size_t staging_bytes) {
         b.hit = (float4*)q;    q += S * 16;
         b.fb = (float2*)q;     q += S * 8;
         b.rayq = (uint32_t*)q; q += S * 16;
-        b.occl = (uint32_t*)q; q += S * 4;
+        b.occl = (uint8_t*)q;  q += S;
         b.stage = (uint8_t*)q; q += S;
         q = (char*)(((uintptr_t)q + 63) & ~(uintptr_t)63);
         b.ctrl = (rtw::WaveCtrl*)q;

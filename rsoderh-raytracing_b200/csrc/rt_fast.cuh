@@ -232,12 +232,19 @@ RT_DEV void prepass(const FastScene& sc, const float4* __restrict__ spre, const 
     if (!sc.hoisted) return;
     const uint32_t box_base = sc.pre_leaves, prim_base = sc.pre_leaves + 2u * sc.pre_boxes;
     // Which boxes would the reference's (un-pruned) walk get through? Parents come first.
+    // A leaf's box lies inside every box above it and, without NaN slabs, the slab test is
+    // monotone in the box: for a "plain" ray the leaf's own box decides alone.
     unsigned long long reached = 0ull;
     for (uint32_t b = 0; b < sc.pre_boxes; b++) {
         const float4 bmin = spre[box_base + 2u * b], bmax = spre[box_base + 2u * b + 1u];
         const uint32_t parent = f_as_u(bmin.w);
-        float t0;
-        const bool ok = box_test(r, bmin, bmax, RT_INFINITY, t0) && (parent == kNone || ((reached >> parent) & 1ull));
+        const bool is_leaf_box = f_as_u(bmax.w) != 0u;
+        bool ok = true;
+        if (is_leaf_box || !r.plain) {
+            float t0;
+            ok = box_test(r, bmin, bmax, RT_INFINITY, t0) &&
+                 (r.plain || parent == kNone || ((reached >> parent) & 1ull));
+        }
         reached |= (unsigned long long)ok << b;
     }
     uint32_t best_leaf = kNone;  // pre-pass leaf the current best came from

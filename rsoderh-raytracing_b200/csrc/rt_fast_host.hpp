@@ -231,7 +231,7 @@ inline void build_fast_layout(const RtSceneDesc& s, FastLayout& out) {
             const uint32_t par = parent[node] >= 0 ? box_index[(size_t)parent[node]] : kNone;
             box_index[node] = pre_boxes++;
             boxes.push_back(make_float4(c.min[0], c.min[1], c.min[2], bits(par)));
-            boxes.push_back(make_float4(c.max[0], c.max[1], c.max[2], 0.f));
+            boxes.push_back(make_float4(c.max[0], c.max[1], c.max[2], bits(c.primitives_len > 0 ? 1u : 0u)));
         }
         for (uint32_t leaf : ana_leaves) {
             const RtBvhNode& n = s.bvh_nodes[leaf];
@@ -248,9 +248,30 @@ inline void build_fast_layout(const RtSceneDesc& s, FastLayout& out) {
                 const RtPrimitiveInfo& info = s.primitives[n.primitives_or_second_child_index + k];
                 if (info.primitive_type == 2u) continue;
                 const uint32_t index = info.primitive_type == 0u ? info.index : s.sphere_count + info.index;
+                out.ana_paths[index] = (uint32_t)out.ana_paths.size();
+                // A primitive whose geometry repeats, bit for bit, an earlier one of the same
+                // leaf that also comes first in the fallback order can never win (strict <):
+                // house.toml holds its ground plane twice.
+                bool shadowed = false;
+                for (uint32_t j = 0; j < k && !shadowed; j++) {
+                    const RtPrimitiveInfo& other = s.primitives[n.primitives_or_second_child_index + j];
+                    if (other.primitive_type != info.primitive_type || other.index >= info.index) continue;
+                    if (info.primitive_type == 0u) {
+                        const RtSphere &a = s.spheres[other.index], &b = s.spheres[info.index];
+                        shadowed = memcmp(a.pos, b.pos, 12) == 0 && memcmp(&a.radius, &b.radius, 4) == 0;
+                    } else {
+                        const RtPlane &a = s.planes[other.index], &b = s.planes[info.index];
+                        shadowed = memcmp(a.pos, b.pos, 12) == 0 && memcmp(a.normal, b.normal, 12) == 0 &&
+                                   memcmp(a.base_change, b.base_change, sizeof a.base_change) == 0;
+                    }
+                }
+                if (shadowed) {
+                    for (size_t j = path.size(); j-- > 0;) out.ana_paths.push_back(path[j]);
+                    out.ana_paths.push_back(kNone);
+                    continue;
+                }
                 for (int j = 0; j < 4; j++) prims.push_back(out.ana[(size_t)index * 4 + j]);
                 pre_prims++;
-                out.ana_paths[index] = (uint32_t)out.ana_paths.size();
                 for (size_t j = path.size(); j-- > 0;) out.ana_paths.push_back(path[j]);
                 out.ana_paths.push_back(kNone);
             }

@@ -79,7 +79,7 @@ struct WaveBuffers {
     float4* sray_d;   // [S] direction of the shadow ray
     float2* fb;       // [S] brute-force fallback winner of the closest-hit ray (t, bits index)
     float4* hit;      // [S] (t, bits rec, u, v) written by the walk kernel
-    uint32_t* occl;   // [S] 1 when the shadow ray is blocked
+    uint8_t* occl;    // [S] 1 when the shadow ray is blocked
     float4* pTL;      // [S][2] throughput + last_pdf, radiance of the current sample + bits rng
     float4* pPI;      // [S][2] pending next-event light + bits flags, bits (pixel, sample, bounce, state)
     uint8_t* stage;   // [S] what the slot needs next (SlotStage)
@@ -202,7 +202,7 @@ RT_DEVONLY void store_path(const WaveParams& p, uint32_t slot, const PathRegs& s
 
 // shader.wgsl:1249-1264: the last next-event sample counts iff nothing blocked its ray.
 RT_DEVONLY void settle_shadow(const WaveParams& p, uint32_t slot, PathRegs& s) {
-    if ((s.flags & kFlagShadow) && lds(&p.b.occl[slot]) == 0u) s.L = s.L + s.pending;
+    if ((s.flags & kFlagShadow) && p.b.occl[slot] == 0) s.L = s.L + s.pending;
     s.flags = 0u;
 }
 
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kShadeThreads, RT_WAVE_SHADE_MIN_BLOCKS) wave_
                 emit_shadow = true;
                 s.flags = kFlagShadow;
                 sts(&p.b.sray_d[slot], make_float4(so.shadow_dir.x, so.shadow_dir.y, so.shadow_dir.z, 0.0f));
-                sts(&p.b.occl[slot], 0u);
+                p.b.occl[slot] = 0;
                 n_shadow++;
             }
             // Both rays start at the hit point (no offset: shader.wgsl:1249, 1295).
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(kPrepassThreads, RT_WAVE_PREPASS_MIN_BLOCKS) w
         walk_begin(p.scene, root_ok, t0_root, best, w);
         const bool walk = w.cur != kNone && !(shadow && best.rec != kNone);
         if (shadow) {
-            if (best.rec != kNone) sts(&p.b.occl[slot], 1u);
+            if (best.rec != kNone) p.b.occl[slot] = 1;
         } else if (walk) {
             p.b.rOD[2u * (size_t)slot + 0u].w = best.t;
             p.b.rOD[2u * (size_t)slot + 1u].w = u_as_f(best.rec);
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(kWalkThreads, RT_WAVE_WALK_MIN_BLOCKS) wave_wa
         const bool finished = busy && (settled || w.cur == kNone);
         if (finished) {
             if (any_hit) {
-                if (best.rec != kNone) sts(&p.b.occl[slot], 1u);
+                if (best.rec != kNone) p.b.occl[slot] = 1;
             } else {
                 if (best.rec == kNone) {
                     const float2 f = lds(&p.b.fb[slot]);
