@@ -306,17 +306,18 @@ RT_DEV void walk_node(const FastScene& sc, const RayCtx& r, Walk& w, uint2* stac
     const float4* q = sc.n2 + 4u * (size_t)w.cur;
     const float4 q0 = ld4(q), q1 = ld4(q + 1), q2 = ld4(q + 2), q3 = ld4(q + 3);
     float t0a, t0b;
-    const uint32_t ra = f_as_u(q0.w), rb = f_as_u(q1.w);
-    const bool pa = box_test(r, q0, q1, w.limit, t0a) && ra != kNone;
-    const bool pb = box_test(r, q2, q3, w.limit, t0b) && rb != kNone;
+    // A missed child is marked by an entry distance no hit can have (t0 <= limit < inf).
+    const float kMiss = __builtin_huge_valf();
+    if (!box_test(r, q0, q1, w.limit, t0a)) t0a = kMiss;
+    if (!box_test(r, q2, q3, w.limit, t0b)) t0b = kMiss;
     const bool second_first = ((r.neg >> f_as_u(q3.w)) & 1u) != 0u;  // shader.wgsl:536
-    const uint32_t rn = second_first ? rb : ra, rf = second_first ? ra : rb;
-    const bool pn = second_first ? pb : pa, pf = second_first ? pa : pb;
-    const float tf0 = second_first ? t0a : t0b;
-    if (pn) {
+    const uint32_t rn = second_first ? f_as_u(q1.w) : f_as_u(q0.w);
+    const uint32_t rf = second_first ? f_as_u(q0.w) : f_as_u(q1.w);
+    const float tn0 = second_first ? t0b : t0a, tf0 = second_first ? t0a : t0b;
+    if (tn0 != kMiss) {
         w.cur = rn;
-        if (pf) stack[w.sp++] = make_uint2(rf, f_as_u(tf0));
-    } else if (pf) {
+        if (tf0 != kMiss) stack[w.sp++] = make_uint2(rf, f_as_u(tf0));
+    } else if (tf0 != kMiss) {
         w.cur = rf;
     } else {
         walk_pop(w, stack);
