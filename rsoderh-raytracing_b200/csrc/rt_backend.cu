@@ -398,15 +398,23 @@ struct RtContext {
     enum Kernel { KERNEL_WAVE, KERNEL_FAST, KERNEL_PIXEL };
     Kernel kernel = KERNEL_WAVE;
     // wavefront pipeline state (rt_wave.cuh)
-    rtw::WaveBuffers wave{};
+    rtw::WaveBuffers wave[2]{};
     void* wave_arena = nullptr;
-    uint32_t wave_slots = 0;          // capacity the arena was allocated for
-    uint32_t wave_max_slots = 8192u * 1024u;
+    uint32_t wave_slots = 0;          // per-group capacity the arena was allocated for
+    int wave_arena_groups = 0;
+    uint32_t* wave_next_path = nullptr;
+    uint32_t wave_max_slots = 8192u * 1024u;  // both groups together
+    int wave_groups = 2;
+    int wave_blocks1[4] = {RT_WAVE_SHADE_MIN_BLOCKS, RT_WAVE_FINISH_MIN_BLOCKS, RT_WAVE_PREPASS_MIN_BLOCKS,
+                           RT_WAVE_WALK_MIN_BLOCKS};  // blocks per SM of shade, finish, pre-pass, walk: one group
+    int wave_blocks2[4] = {8, 8, 4, 4};               // ... two groups (measured best: full grids on both streams)
     void* wave_staging = nullptr;     // per-sample radiance planes of the current batch
     size_t wave_staging_bytes = 0;
     size_t wave_staging_budget = (size_t)8192 << 20;
-    uint32_t* wave_live_host = nullptr;  // pinned read-back of WaveCtrl::live, one word per chunk in flight
-    cudaEvent_t wave_events[2] = {nullptr, nullptr};
+    uint32_t* wave_live_host = nullptr;  // pinned read-back of WaveCtrl::live: [2 chunks in flight][2 groups]
+    cudaStream_t wave_streams[2] = {nullptr, nullptr};
+    cudaEvent_t wave_events[2][2] = {};
+    cudaEvent_t wave_fork = nullptr, wave_phase = nullptr, wave_join[2] = {nullptr, nullptr};
     bool profiling = false;
     RtWaveProfile profile{};
     bool detailed = false;
@@ -514,32 +522,37 @@ bool validate_bvh(const RtSceneDesc& s, uint32_t* depth_out, std::string* why) {
 }
 
 // ---- wavefront pipeline (rt_wave.cuh): buffers and the wave loop ----
-int wave_reserve(RtContext* ctx, uint32_t slots, size_t staging_bytes) {
-    if (!(ctx->wave_arena && ctx->wave_slots >= slots)) {
-        RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+int wave_reserve(RtContext* ctx, uint32_t slots, int groups, size_t staging_bytes) {
+    if (!(ctx->wave_arena && ctx->wave_slots >= slots && ctx->wave_arena_groups == groups)) {
+        RT_CUDA(ctx, cudaDeviceSynchronize());
         cudaFree(ctx->wave_arena);
         ctx->wave_arena = nullptr;
         ctx->wave_slots = 0;
         const size_t S = slots;
-        // 8 x 16-byte arrays + fb (8) + occl (4) + rayq (4 x 4) + stage (1) + ctrl
-        RT_CUDA(ctx, cudaMalloc(&ctx->wave_arena, S * (8 * 16 + 8 + 4 + 16 + 1) + 512));
-        char* q = (char*)ctx->wave_arena;
-        rtw::WaveBuffers& b = ctx->wave;
-        b.rOD = (float4*)q;    q += S * 32;
-        b.pTL = (float4*)q;    q += S * 32;
-        b.pPI = (float4*)q;    q += S * 32;
-        b.sray_d = (float4*)q; q += S * 16;
-        b.hit = (float4*)q;    q += S * 16;
-        b.fb = (float2*)q;     q += S * 8;
-        b.rayq = (uint32_t*)q; q += S * 16;
-        b.occl = (uint8_t*)q;  q += S;
-        b.stage = (uint8_t*)q; q += S;
-        q = (char*)(((uintptr_t)q + 63) & ~(uintptr_t)63);
-        b.ctrl = (rtw::WaveCtrl*)q;
+        // per group: 3 x 32-byte pair arrays + 2 x 16 + fb (8) + rayq (4 x 4) + occl (1) + stage (1) + ctrl
+        const size_t per_group = (S * (3 * 32 + 2 * 16 + 8 + 16 + 2) + 1024 + 255) & ~(size_t)255;
+        RT_CUDA(ctx, cudaMalloc(&ctx->wave_arena, per_group * (size_t)groups + 256));
+        for (int g = 0; g < groups; g++) {
+            char* q = (char*)ctx->wave_arena + per_group * (size_t)g;
+            rtw::WaveBuffers& b = ctx->wave[g];
+            b.rOD = (float4*)q;    q += S * 32;
+            b.pTL = (float4*)q;    q += S * 32;
+            b.pPI = (float4*)q;    q += S * 32;
+            b.sray_d = (float4*)q; q += S * 16;
+            b.hit = (float4*)q;    q += S * 16;
+            b.fb = (float2*)q;     q += S * 8;
+            b.rayq = (uint32_t*)q; q += S * 16;
+            b.occl = (uint8_t*)q;  q += S;
+            b.stage = (uint8_t*)q; q += S;
+            q = (char*)(((uintptr_t)q + 63) & ~(uintptr_t)63);
+            b.ctrl = (rtw::WaveCtrl*)q;
+        }
+        ctx->wave_next_path = (uint32_t*)((char*)ctx->wave_arena + per_group * (size_t)groups);
         ctx->wave_slots = slots;
+        ctx->wave_arena_groups = groups;
     }
     if (!(ctx->wave_staging && ctx->wave_staging_bytes >= staging_bytes)) {
-        RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        RT_CUDA(ctx, cudaDeviceSynchronize());
         cudaFree(ctx->wave_staging);
         ctx->wave_staging = nullptr;
         ctx->wave_staging_bytes = 0;
@@ -551,96 +564,148 @@ int wave_reserve(RtContext* ctx, uint32_t slots, size_t staging_bytes) {
 
 // Renders the sample range in batches. Inside a batch the paths are independent work items
 // handed to the slots as they free up; waves run until every slot has retired, then the
-// staged samples are added to the accumulation buffer in sample order. The host only paces
-// the launches: it reads the live-slot count one chunk behind, so the stream never runs dry.
+// staged samples are added to the accumulation buffer in sample order. The slots form two
+// groups on two streams, started half a wave apart. The host only paces the launches: it
+// reads the live-slot counts one chunk behind, so the streams never run dry.
 int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, uint32_t sample_count,
                 uint32_t max_bounces) {
-    rtw::WaveParams p;
-    memset(&p, 0, sizeof p);
-    p.scene = ctx->fast;
-    p.env.texture = e.texture;
-    p.env.alias = e.d_alias;
-    p.env.texels = e.d_texels;
-    p.env.width = e.width;
-    p.env.height = e.height;
-    p.camera = ctx->camera;
-    p.accum = ctx->d_accum;
-    p.counters = ctx->d_counters;
-    p.width = ctx->width;
-    p.height = ctx->height;
-    p.tiles_x = (ctx->width + 7u) / 8u;
-    p.pixel_ids = p.tiles_x * ((ctx->height + 7u) / 8u) * 64u;
-    p.max_bounces = max_bounces;
+    rtw::WaveParams base;
+    memset(&base, 0, sizeof base);
+    base.scene = ctx->fast;
+    base.env.texture = e.texture;
+    base.env.alias = e.d_alias;
+    base.env.texels = e.d_texels;
+    base.env.width = e.width;
+    base.env.height = e.height;
+    base.camera = ctx->camera;
+    base.accum = ctx->d_accum;
+    base.counters = ctx->d_counters;
+    base.width = ctx->width;
+    base.height = ctx->height;
+    base.tiles_x = (ctx->width + 7u) / 8u;
+    base.pixel_ids = base.tiles_x * ((ctx->height + 7u) / 8u) * 64u;
+    base.max_bounces = max_bounces;
 
     // Batch size: as many samples as the staging budget holds, and path indices must fit 32 bits.
     const size_t pixels = (size_t)ctx->width * ctx->height;
     uint64_t batch = ctx->wave_staging_budget / (pixels * sizeof(float4));
-    const uint64_t index_cap = 0xFFFF0000ull / p.pixel_ids;
+    const uint64_t index_cap = 0xFFFF0000ull / base.pixel_ids;
     if (batch > index_cap) batch = index_cap;
     if (batch > sample_count) batch = sample_count;
     if (batch < 1) batch = 1;
-    const uint64_t paths_per_batch = (uint64_t)p.pixel_ids * batch;
-    p.slots = (uint32_t)(paths_per_batch < ctx->wave_max_slots ? paths_per_batch : ctx->wave_max_slots);
-    int st = wave_reserve(ctx, p.slots, pixels * sizeof(float4) * (size_t)batch);
+    const uint64_t paths_per_batch = (uint64_t)base.pixel_ids * batch;
+    const uint32_t total_slots = (uint32_t)(paths_per_batch < ctx->wave_max_slots ? paths_per_batch : ctx->wave_max_slots);
+    const int groups = (ctx->wave_groups >= 2 && total_slots >= 262144u) ? 2 : 1;  // small frames: one group
+    const uint32_t per_group = (total_slots + (uint32_t)groups - 1u) / (uint32_t)groups;
+    int st = wave_reserve(ctx, per_group, groups, pixels * sizeof(float4) * (size_t)batch);
     if (st != RT_OK) return st;
-    p.b = ctx->wave;
-    p.staging = (float4*)ctx->wave_staging;
 
+    rtw::WaveParams p[2];
+    for (int g = 0; g < groups; g++) {
+        p[g] = base;
+        p[g].b = ctx->wave[g];
+        p[g].slots = per_group;
+        p[g].staging = (float4*)ctx->wave_staging;
+        p[g].next_path = ctx->wave_next_path;
+    }
     auto blocks_for = [&](uint32_t items, int threads, int per_sm) {
         unsigned need = (items + (unsigned)threads - 1u) / (unsigned)threads;
         unsigned cap = (unsigned)ctx->sm_count * (unsigned)per_sm;
         return need < cap ? (need ? need : 1u) : cap;
     };
-    const unsigned shade_blocks = blocks_for(p.slots, rtw::kShadeThreads, RT_WAVE_SHADE_MIN_BLOCKS);
-    const unsigned finish_blocks = blocks_for(p.slots, rtw::kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS);
-    const unsigned prepass_blocks = blocks_for(2u * p.slots, rtw::kPrepassThreads, RT_WAVE_PREPASS_MIN_BLOCKS);
-    const unsigned walk_blocks = blocks_for(2u * p.slots, rtw::kWalkThreads, RT_WAVE_WALK_MIN_BLOCKS);
-    cudaStream_t s = ctx->stream;
+    // Blocks per SM are tunable per group count (RT_WAVE_BLOCKS2); full-size grids on both
+    // streams measured best, the block scheduler interleaves the two kernels as SMs free up.
+    const int* per_sm = groups == 2 ? ctx->wave_blocks2 : ctx->wave_blocks1;
+    const unsigned shade_blocks = blocks_for(per_group, rtw::kShadeThreads, per_sm[0]);
+    const unsigned finish_blocks = blocks_for(per_group, rtw::kFinishThreads, per_sm[1]);
+    const unsigned prepass_blocks = blocks_for(2u * per_group, rtw::kPrepassThreads, per_sm[2]);
+    const unsigned walk_blocks = blocks_for(2u * per_group, rtw::kWalkThreads, per_sm[3]);
 
     // RT_WAVE_TIMELINE=1 (diagnostics) or rt_set_profiling: CUDA events around every kernel.
     static const bool timeline_print = getenv("RT_WAVE_TIMELINE") != nullptr;
     const bool timeline = timeline_print || ctx->profiling;
-    std::vector<cudaEvent_t> tl;
-    auto mark = [&]() {
+    std::vector<cudaEvent_t> tl[2];
+    auto mark = [&](int g, cudaStream_t s) {
         if (!timeline) return;
         cudaEvent_t ev;
         cudaEventCreate(&ev);
         cudaEventRecord(ev, s);
-        tl.push_back(ev);
+        tl[g].push_back(ev);
+    };
+    // One wave of group g: kernels first .. last-1 of (shade, finish, pre-pass, walk).
+    auto launch = [&](int g, uint32_t wave, int first, int last) {
+        cudaStream_t s = groups == 2 ? ctx->wave_streams[g] : ctx->stream;
+        p[g].wave = wave;
+        for (int k = first; k < last; k++) {
+            mark(g, s);
+            if (k == 0) rtw::wave_shade_kernel<<<shade_blocks, rtw::kShadeThreads, 0, s>>>(p[g]);
+            else if (k == 1) rtw::wave_finish_kernel<<<finish_blocks, rtw::kFinishThreads, 0, s>>>(p[g]);
+            else if (k == 2) rtw::wave_prepass_kernel<<<prepass_blocks, rtw::kPrepassThreads, 0, s>>>(p[g]);
+            else rtw::wave_walk_kernel<<<walk_blocks, rtw::kWalkThreads, 0, s>>>(p[g]);
+            mark(g, s);
+            ctx->launches++;
+        }
     };
 
     int status = RT_OK;
+    cudaEvent_t t_begin = nullptr, t_end = nullptr;
+    if (timeline) {
+        cudaEventCreate(&t_begin);
+        cudaEventCreate(&t_end);
+        cudaEventRecord(t_begin, ctx->stream);
+    }
     for (uint32_t done = 0; done < sample_count && status == RT_OK; done += (uint32_t)batch) {
-        p.batch_begin = sample_begin + done;
-        p.batch_count = (uint32_t)(sample_count - done < batch ? sample_count - done : batch);
-        p.path_total = p.pixel_ids * p.batch_count;
-        rtw::wave_init_kernel<<<(p.slots + 255) / 256, 256, 0, s>>>(p);
-        ctx->launches++;
+        for (int g = 0; g < groups; g++) {
+            p[g].batch_begin = sample_begin + done;
+            p[g].batch_count = (uint32_t)(sample_count - done < batch ? sample_count - done : batch);
+            p[g].path_total = base.pixel_ids * p[g].batch_count;
+        }
+        cudaMemsetAsync(ctx->wave_next_path, 0, sizeof(uint32_t), ctx->stream);
+        if (groups == 2) {
+            // fork: both group streams start after everything queued on the context's stream
+            cudaEventRecord(ctx->wave_fork, ctx->stream);
+            for (int g = 0; g < 2; g++) cudaStreamWaitEvent(ctx->wave_streams[g], ctx->wave_fork, 0);
+        }
+        for (int g = 0; g < groups; g++) {
+            cudaStream_t s = groups == 2 ? ctx->wave_streams[g] : ctx->stream;
+            rtw::wave_init_kernel<<<(per_group + 255) / 256, 256, 0, s>>>(p[g]);
+            ctx->launches++;
+        }
 
         const uint32_t chunk = 8;
         uint32_t wave = 0;
         for (uint32_t k = 0;; k++) {
             for (uint32_t i = 0; i < chunk; i++, wave++) {
-                p.wave = wave;
-                mark();
-                rtw::wave_shade_kernel<<<shade_blocks, rtw::kShadeThreads, 0, s>>>(p);
-                mark();
-                rtw::wave_finish_kernel<<<finish_blocks, rtw::kFinishThreads, 0, s>>>(p);
-                mark();
-                rtw::wave_prepass_kernel<<<prepass_blocks, rtw::kPrepassThreads, 0, s>>>(p);
-                mark();
-                rtw::wave_walk_kernel<<<walk_blocks, rtw::kWalkThreads, 0, s>>>(p);
-                mark();
-                ctx->launches += 4;
+                if (groups == 1) {
+                    launch(0, wave, 0, 4);
+                } else if (wave == 0) {
+                    // Group 1 starts half a wave late: its shade + finish run beside group 0's
+                    // pre-pass + walk from then on.
+                    launch(0, 0, 0, 2);
+                    cudaEventRecord(ctx->wave_phase, ctx->wave_streams[0]);
+                    cudaStreamWaitEvent(ctx->wave_streams[1], ctx->wave_phase, 0);
+                    launch(0, 0, 2, 4);
+                    launch(1, 0, 0, 2);
+                } else {
+                    launch(0, wave, 0, 4);
+                    launch(1, wave - 1, 2, 4);
+                    launch(1, wave, 0, 2);
+                }
             }
             cudaError_t ce = cudaGetLastError();
-            if (ce == cudaSuccess)
-                ce = cudaMemcpyAsync(&ctx->wave_live_host[k & 1u], &p.b.ctrl->live, sizeof(uint32_t),
+            for (int g = 0; g < groups && ce == cudaSuccess; g++) {
+                cudaStream_t s = groups == 2 ? ctx->wave_streams[g] : ctx->stream;
+                ce = cudaMemcpyAsync(&ctx->wave_live_host[(k & 1u) * 2 + g], &p[g].b.ctrl->live, sizeof(uint32_t),
                                      cudaMemcpyDeviceToHost, s);
-            if (ce == cudaSuccess) ce = cudaEventRecord(ctx->wave_events[k & 1u], s);
+                if (ce == cudaSuccess) ce = cudaEventRecord(ctx->wave_events[k & 1u][g], s);
+            }
             if (ce == cudaSuccess && k > 0) {
-                ce = cudaEventSynchronize(ctx->wave_events[(k - 1u) & 1u]);
-                if (ce == cudaSuccess && ctx->wave_live_host[(k - 1u) & 1u] == 0u) break;  // the last chunk ran empty
+                uint32_t live = 0;
+                for (int g = 0; g < groups && ce == cudaSuccess; g++) {
+                    ce = cudaEventSynchronize(ctx->wave_events[(k - 1u) & 1u][g]);
+                    live += ctx->wave_live_host[((k - 1u) & 1u) * 2 + g];
+                }
+                if (ce == cudaSuccess && live == 0u) break;  // the last chunk ran empty
             }
             if (ce != cudaSuccess) {
                 status = fail(ctx, RT_ERR_CUDA, "wave launch failed: %s", cudaGetErrorString(ce));
@@ -651,51 +716,67 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
                 break;
             }
         }
+        if (groups == 2) {
+            // join: the context's stream waits for both groups (group 1's last half wave is empty)
+            for (int g = 0; g < 2; g++) {
+                cudaEventRecord(ctx->wave_join[g], ctx->wave_streams[g]);
+                cudaStreamWaitEvent(ctx->stream, ctx->wave_join[g], 0);
+            }
+        }
         if (status == RT_OK) {
-            rtw::wave_accumulate_kernel<<<(unsigned)((pixels + 255) / 256), 256, 0, s>>>(p);
+            rtw::wave_accumulate_kernel<<<(unsigned)((pixels + 255) / 256), 256, 0, ctx->stream>>>(p[0]);
             ctx->launches++;
             cudaError_t ce = cudaGetLastError();
             if (ce != cudaSuccess) status = fail(ctx, RT_ERR_CUDA, "accumulate launch failed: %s", cudaGetErrorString(ce));
         }
     }
 
-    if (timeline && !tl.empty()) {
-        cudaStreamSynchronize(s);
-        double sum[5] = {0, 0, 0, 0, 0};
-        float total = 0.f;
-        cudaEventElapsedTime(&total, tl.front(), tl.back());
-        const size_t waves = tl.size() / 5;
-        for (size_t w = 0; w < waves; w++) {
-            for (int j = 0; j < 4; j++) {
+    if (timeline) {
+        cudaEventRecord(t_end, ctx->stream);
+        cudaEventSynchronize(t_end);
+        double sum[4] = {0, 0, 0, 0};
+        uint64_t count[4] = {0, 0, 0, 0};
+        size_t waves = 0;
+        for (int g = 0; g < groups; g++) {
+            // events come in (before, after) pairs; kernel kind cycles shade, finish, pre-pass, walk
+            // (group 1 of a two-group render starts its cycle at shade as well)
+            const size_t n = tl[g].size() / 2;
+            for (size_t i = 0; i < n; i++) {
                 float ms = 0.f;
-                cudaEventElapsedTime(&ms, tl[w * 5 + j], tl[w * 5 + j + 1]);
-                sum[j] += ms;
+                cudaEventElapsedTime(&ms, tl[g][2 * i], tl[g][2 * i + 1]);
+                const int kind = (int)(i % 4);
+                sum[kind] += ms;
+                count[kind]++;
             }
-            if (w + 1 < waves) {
-                float ms = 0.f;
-                cudaEventElapsedTime(&ms, tl[w * 5 + 4], tl[(w + 1) * 5]);
-                sum[4] += ms;
-            }
+            if (g == 0) waves = n / 4;
         }
+        float total = 0.f;
+        cudaEventElapsedTime(&total, t_begin, t_end);
         ctx->profile.renders++;
         ctx->profile.waves += waves;
+        double busy = 0;
         for (int j = 0; j < 4; j++) {
-            ctx->profile.launches[j] += waves;
+            ctx->profile.launches[j] += count[j];
             ctx->profile.kernel_ms[j] += sum[j];
+            busy += sum[j];
         }
-        ctx->profile.gap_ms += sum[4];
+        ctx->profile.gap_ms += groups == 1 ? total - busy : 0.0;
         ctx->profile.total_ms += total;
         if (timeline_print) {
-            fprintf(stderr, "[wave timeline] slots=%u waves=%zu total=%.3f ms | shade %.3f finish %.3f prepass %.3f walk %.3f gaps %.3f ms\n",
-                    p.slots, waves, total, sum[0], sum[1], sum[2], sum[3], sum[4]);
-            for (size_t w = 0; w < waves; w += (waves / 12 ? waves / 12 : 1)) {
+            fprintf(stderr, "[wave timeline] groups=%d slots=%u x %d waves=%zu total=%.3f ms | shade %.3f finish %.3f prepass %.3f walk %.3f (sum %.3f) ms\n",
+                    groups, per_group, groups, waves, total, sum[0], sum[1], sum[2], sum[3], busy);
+            const size_t n = tl[0].size() / 8;
+            for (size_t w = 0; w < n; w += (n / 10 ? n / 10 : 1)) {
                 float t[4];
-                for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], tl[w * 5 + j], tl[w * 5 + j + 1]);
+                for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], tl[0][8 * w + 2 * j], tl[0][8 * w + 2 * j + 1]);
                 fprintf(stderr, "   wave %4zu: shade %7.1f finish %7.1f prepass %7.1f walk %7.1f us\n", w, t[0] * 1e3,
                         t[1] * 1e3, t[2] * 1e3, t[3] * 1e3);
             }
         }
-        for (cudaEvent_t ev : tl) cudaEventDestroy(ev);
+        for (int g = 0; g < 2; g++)
+            for (cudaEvent_t ev : tl[g]) cudaEventDestroy(ev);
+        cudaEventDestroy(t_begin);
+        cudaEventDestroy(t_end);
     }
     return status;
 }
@@ -792,11 +873,27 @@ int rt_create(int device, RtContext** out) {
         long v = atol(k);
         if (v >= 1 && v <= (1l << 18)) ctx->wave_staging_budget = (size_t)v << 20;
     }
-    if ((e = cudaHostAlloc(&ctx->wave_live_host, 2 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess)
+    if (const char* k = getenv("RT_WAVE_GROUPS")) ctx->wave_groups = atoi(k) >= 2 ? 2 : 1;
+    if (const char* k = getenv("RT_WAVE_BLOCKS2")) {  // e.g. "4,4,2,2"
+        int v[4];
+        if (sscanf(k, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4)
+            for (int i = 0; i < 4; i++)
+                if (v[i] >= 1 && v[i] <= 16) ctx->wave_blocks2[i] = v[i];
+    }
+    if ((e = cudaHostAlloc(&ctx->wave_live_host, 4 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess)
         return bail("cudaHostAlloc", e);
-    for (int i = 0; i < 2; i++)
-        if ((e = cudaEventCreateWithFlags(&ctx->wave_events[i], cudaEventDisableTiming)) != cudaSuccess)
+    for (int g = 0; g < 2; g++) {
+        if ((e = cudaStreamCreateWithFlags(&ctx->wave_streams[g], cudaStreamNonBlocking)) != cudaSuccess)
+            return bail("cudaStreamCreate", e);
+        if ((e = cudaEventCreateWithFlags(&ctx->wave_join[g], cudaEventDisableTiming)) != cudaSuccess)
             return bail("cudaEventCreate", e);
+        for (int i = 0; i < 2; i++)
+            if ((e = cudaEventCreateWithFlags(&ctx->wave_events[i][g], cudaEventDisableTiming)) != cudaSuccess)
+                return bail("cudaEventCreate", e);
+    }
+    if ((e = cudaEventCreateWithFlags(&ctx->wave_fork, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->wave_phase, cudaEventDisableTiming)) != cudaSuccess)
+        return bail("cudaEventCreate", e);
     *out = ctx;
     return RT_OK;
 }
@@ -812,8 +909,14 @@ void rt_destroy(RtContext* ctx) {
     cudaFree(ctx->wave_arena);
     if (ctx->wave_live_host) cudaFreeHost(ctx->wave_live_host);
     cudaFree(ctx->wave_staging);
-    for (int i = 0; i < 2; i++)
-        if (ctx->wave_events[i]) cudaEventDestroy(ctx->wave_events[i]);
+    for (int g = 0; g < 2; g++) {
+        for (int i = 0; i < 2; i++)
+            if (ctx->wave_events[i][g]) cudaEventDestroy(ctx->wave_events[i][g]);
+        if (ctx->wave_join[g]) cudaEventDestroy(ctx->wave_join[g]);
+        if (ctx->wave_streams[g]) cudaStreamSynchronize(ctx->wave_streams[g]), cudaStreamDestroy(ctx->wave_streams[g]);
+    }
+    if (ctx->wave_fork) cudaEventDestroy(ctx->wave_fork);
+    if (ctx->wave_phase) cudaEventDestroy(ctx->wave_phase);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

@@ -17,7 +17,9 @@
 // compacting inside the warp (ballot + a small shared-memory list), so a warp's 32 lanes work
 // on 32 NEARBY slots: full lanes and coalesced state traffic, no global lists.
 // The bounce ray and the shadow ray of one hit do not depend on each other and travel in
-// the same wave. Path state lives in global memory (~170 B per slot).
+// the same wave. The slots are split into two groups whose waves run half a wave apart on
+// two streams, so one group's memory-bound shade / finish overlaps the other's issue-bound
+// pre-pass / walk. Path state lives in global memory (~170 B per slot).
 //
 // Paths are independent work items: a slot that finishes a path takes the next path index
 // from a global counter (sample-major, pixels in 8x8-tile order inside a sample), so the
@@ -66,8 +68,7 @@ struct WaveCtrl {
     uint32_t ray_n[2];
     uint32_t ray_head[2];
     uint32_t live;       // slots not yet retired
-    uint32_t next_path;  // next path index of the batch to hand out
-    uint32_t pad[2];
+    uint32_t pad[3];
 };
 
 struct WaveBuffers {
@@ -97,6 +98,7 @@ struct WaveParams {
     uint32_t width, height;
     uint32_t tiles_x, pixel_ids;  // 8x8-tile-major pixel numbering (ids of partial tiles included)
     float4* staging;       // [batch_count][width * height] radiance of each finished sample
+    uint32_t* next_path;   // next path index of the batch to hand out (shared by all slot groups)
     uint32_t slots;
     uint32_t batch_begin, batch_count;  // the samples of this batch
     uint32_t path_total;   // batch_count * pixel_ids path indices (ids of partial tiles are skipped)
@@ -173,7 +175,6 @@ __global__ void wave_init_kernel(const WaveParams p) {
         WaveCtrl c;
         memset(&c, 0, sizeof c);
         c.live = p.slots;
-        c.next_path = 0u;
         *p.b.ctrl = c;
     }
 }
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wav
                 const uint32_t lane = threadIdx.x & 31u;
                 const int leader = __ffs(m) - 1;
                 uint32_t base = 0;
-                if ((int)lane == leader) base = atomicAdd(&c->next_path, (uint32_t)__popc(m));
+                if ((int)lane == leader) base = atomicAdd(p.next_path, (uint32_t)__popc(m));
                 base = __shfl_sync(0xFFFFFFFFu, base, leader);
                 if (on) q = base + __popc(m & ((1u << lane) - 1u));
             }
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wav
         if (on) {
             uint32_t px = 0, py = 0;
             // ids of partial tiles name no pixel: draw again (only for sizes not divisible by 8)
-            while (q < p.path_total && !pixel_of_id(p, q % p.pixel_ids, px, py)) q = atomicAdd(&c->next_path, 1u);
+            while (q < p.path_total && !pixel_of_id(p, q % p.pixel_ids, px, py)) q = atomicAdd(p.next_path, 1u);
             if (q >= p.path_total) {
                 I.w = SLOT_RETIRED;
                 p.b.stage[slot] = STAGE_IDLE;
