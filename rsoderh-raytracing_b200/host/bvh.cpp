@@ -6,8 +6,15 @@
 // Differences in mechanism only: the reference builds a boxed tree and flattens it in
 // a second pre-order pass (bvh.rs:155-178); here nodes are emitted directly in
 // pre-order while recursing, which yields the identical array. Primitive bounds and
-// centroids are computed once instead of per query (same f32 values).
+// centroids are computed once instead of per query (same f32 values). Large subtrees are
+// built on separate threads into their own arrays (indices relative to the subtree) and
+// spliced in pre-order with the offsets added: the two children of a node work on disjoint
+// primitive ranges and a subtree's content does not depend on where it ends up, so the
+// result is the serial one byte for byte.
+#include <cstdlib>
 #include <cstring>
+#include <future>
+#include <thread>
 
 #include "scene.hpp"
 
@@ -23,10 +30,27 @@ struct BuildPrim {
     Vec3 center;
 };
 
+constexpr size_t kParallelMin = 1u << 16;  // subtrees below this many primitives stay on their thread
+
 struct Builder {
     std::vector<BuildPrim>& prims;
     std::vector<RtPrimitiveInfo>& ordered;
     std::vector<RtBvhNode>& nodes;
+    int tasks_left = 0;  // how many more times this subtree may fork
+
+    // Appends a subtree built with indices relative to itself: node indices move by the
+    // position it lands at, leaf slots by `slot_base`.
+    void splice(const std::vector<RtBvhNode>& sub_nodes, const std::vector<RtPrimitiveInfo>& sub_ordered,
+                uint32_t slot_base) {
+        const uint32_t node_base = (uint32_t)nodes.size();
+        const uint32_t slot_shift = slot_base;  // sub slots start at 0
+        nodes.reserve(nodes.size() + sub_nodes.size());
+        for (RtBvhNode n : sub_nodes) {
+            n.primitives_or_second_child_index += n.primitives_len > 0 ? slot_shift : node_base;
+            nodes.push_back(n);
+        }
+        ordered.insert(ordered.end(), sub_ordered.begin(), sub_ordered.end());
+    }
 
     static RtBvhNode make_node(const Bounds3& b, uint32_t idx, uint32_t len, uint32_t axis) {
         RtBvhNode n;
@@ -137,9 +161,26 @@ struct Builder {
         size_t node_index = nodes.size();
         nodes.push_back(make_node(bounds, 0, 0, (uint32_t)axis));
         uint32_t d0 = 0, d1 = 0;
-        Bounds3 left = build(begin, split_index, &d0);
-        uint32_t second_child = (uint32_t)nodes.size();
-        Bounds3 right = build(split_index, end, &d1);
+        Bounds3 left, right;
+        uint32_t second_child;
+        if (count >= kParallelMin && tasks_left > 0) {
+            // Build both children into private arrays, the left one on another thread.
+            tasks_left--;
+            std::vector<RtPrimitiveInfo> lo, ro;
+            std::vector<RtBvhNode> ln, rn;
+            Builder lb{prims, lo, ln, tasks_left / 2}, rb{prims, ro, rn, tasks_left - tasks_left / 2};
+            auto fut = std::async(std::launch::async, [&] { return lb.build(begin, split_index, &d0); });
+            right = rb.build(split_index, end, &d1);
+            left = fut.get();
+            const uint32_t slot0 = (uint32_t)ordered.size();
+            splice(ln, lo, slot0);
+            second_child = (uint32_t)nodes.size();
+            splice(rn, ro, slot0 + (uint32_t)lo.size());
+        } else {
+            left = build(begin, split_index, &d0);
+            second_child = (uint32_t)nodes.size();
+            right = build(split_index, end, &d1);
+        }
         // BvhBuildNode::new_interior: bounds = union of the children (bvh.rs:197-203).
         Bounds3 node_bounds = Bounds3::identity().unite(left).unite(right);
         nodes[node_index] = make_node(node_bounds, second_child, 0, (uint32_t)axis);
@@ -183,7 +224,11 @@ void build_bvh(HostScene& scene) {
     scene.bvh_depth = 0;
     if (prims.empty()) throw SceneError(RT_ERR_SCENE, "scene has no primitives");  // bvh.rs:222
     scene.u_primitives.reserve(prims.size());
-    Builder builder{prims, scene.u_primitives, scene.u_nodes};
+    int threads = (int)std::thread::hardware_concurrency();
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    if (const char* k = std::getenv("RT_BVH_THREADS")) threads = std::atoi(k) > 0 ? std::atoi(k) : 1;
+    Builder builder{prims, scene.u_primitives, scene.u_nodes, threads - 1};
     builder.build(0, prims.size(), &scene.bvh_depth);
 }
 

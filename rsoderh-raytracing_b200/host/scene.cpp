@@ -2,6 +2,9 @@
 // Follows src/scene.rs:235-252 (load_toml), 264-322 (descriptors), 324-441
 // (build_scene), 190-201 (Plane::to_uniform) and src/mesh.rs:92-113 (pack_meshes).
 #include <cmath>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "scene.hpp"
@@ -132,7 +135,13 @@ void HostScene::finalize() {
         for (Vec3 n : mesh.normals) u_normals.push_back(RtVec3{n.x, n.y, n.z, 0.f});
     }
 
+    const bool timing = std::getenv("RT_HOST_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
     build_bvh(*this);
+    if (timing)
+        std::fprintf(stderr, "[host] build_bvh: %.3f s for %zu primitives, %zu nodes\n",
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(),
+                     u_primitives.size(), u_nodes.size());
     finalized = true;
 }
 

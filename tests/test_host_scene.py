@@ -283,3 +283,15 @@ def test_shipped_scene_cameras(house, default_scene):
         assert s.camera.pos == (0.0, 1.0, 3.0)
         assert s.camera.yaw == 0.0 and s.camera.pitch == 0.0
         assert np.float32(s.camera.fov_y) == np.float32(100.0) * np.float32(math.pi / 180.0)
+
+
+def test_parallel_bvh_build_is_byte_identical(rt, monkeypatch):
+    # Subtrees of >= 65536 primitives are built on their own threads and spliced in
+    # pre-order (host/bvh.cpp); the arrays must be the serial build's byte for byte.
+    dumps = {}
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("RT_BVH_THREADS", threads)
+        scene = rt.Scene.synthetic_field(ASSETS, 14)  # 200 k triangles: three levels fork
+        assert scene.counts()["triangles"] > 150000
+        dumps[threads] = (scene.bvh_nodes_words().tobytes(), scene.primitives_words().tobytes(), scene.bvh_depth)
+    assert dumps["1"] == dumps["3"] == dumps["8"]
