@@ -536,8 +536,7 @@ int wave_reserve(RtContext* ctx, uint32_t slots, int groups, size_t staging_byte
             char* q = (char*)ctx->wave_arena + per_group * (size_t)g;
             rtw::WaveBuffers& b = ctx->wave[g];
             b.rOD = (float4*)q;    q += S * 32;
-            b.pTL = (float4*)q;    q += S * 32;
-            b.pPI = (float4*)q;    q += S * 32;
+            b.pTLPI = (float4*)q;  q += S * 64;
             b.sray_d = (float4*)q; q += S * 16;
             b.hit = (float4*)q;    q += S * 16;
             b.fb = (float2*)q;     q += S * 8;

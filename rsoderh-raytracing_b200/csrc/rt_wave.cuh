@@ -81,8 +81,9 @@ struct WaveBuffers {
     float2* fb;       // [S] brute-force fallback winner of the closest-hit ray (t, bits index)
     float4* hit;      // [S] (t, bits rec, u, v) written by the walk kernel
     uint8_t* occl;    // [S] 1 when the shadow ray is blocked
-    float4* pTL;      // [S][2] throughput + last_pdf, radiance of the current sample + bits rng
-    float4* pPI;      // [S][2] pending next-event light + bits flags, bits (pixel, sample, bounce, state)
+    float4* pTLPI;    // [S][4] 64 contiguous bytes only shade / finish touch: throughput + last_pdf,
+                      //        radiance of the current sample + bits rng, pending next-event light +
+                      //        bits flags, bits (pixel, sample, bounce, state)
     uint8_t* stage;   // [S] what the slot needs next (SlotStage)
     uint32_t* rayq;   // [2][2S]
     WaveCtrl* ctrl;
@@ -168,7 +169,7 @@ RT_DEVONLY void list_push2(uint32_t* list, uint32_t* count, bool want_a, uint32_
 __global__ void wave_init_kernel(const WaveParams p) {
     uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot < p.slots) {
-        sts((uint4*)&p.b.pPI[2u * (size_t)slot + 1u], make_uint4(0u, 0u, 0u, SLOT_NEW));
+        sts((uint4*)&p.b.pTLPI[4u * (size_t)slot + 3u], make_uint4(0u, 0u, 0u, SLOT_NEW));
         p.b.stage[slot] = STAGE_FINISH;  // every slot starts its first path in wave 0's finish pass
     }
     if (slot == 0) {
@@ -186,7 +187,7 @@ struct PathRegs {
 };
 
 RT_DEVONLY void load_path(const WaveParams& p, uint32_t slot, PathRegs& s) {
-    const float4 t4 = lds(&p.b.pTL[2u * (size_t)slot + 0u]), l4 = lds(&p.b.pTL[2u * (size_t)slot + 1u]), p4 = lds(&p.b.pPI[2u * (size_t)slot + 0u]);
+    const float4 t4 = lds(&p.b.pTLPI[4u * (size_t)slot + 0u]), l4 = lds(&p.b.pTLPI[4u * (size_t)slot + 1u]), p4 = lds(&p.b.pTLPI[4u * (size_t)slot + 2u]);
     s.T = xyz(t4);
     s.last_pdf = t4.w;
     s.L = xyz(l4);
@@ -196,9 +197,9 @@ RT_DEVONLY void load_path(const WaveParams& p, uint32_t slot, PathRegs& s) {
 }
 
 RT_DEVONLY void store_path(const WaveParams& p, uint32_t slot, const PathRegs& s) {
-    sts(&p.b.pTL[2u * (size_t)slot + 0u], make_float4(s.T.x, s.T.y, s.T.z, s.last_pdf));
-    sts(&p.b.pTL[2u * (size_t)slot + 1u], make_float4(s.L.x, s.L.y, s.L.z, u_as_f(s.rng)));
-    sts(&p.b.pPI[2u * (size_t)slot + 0u], make_float4(s.pending.x, s.pending.y, s.pending.z, u_as_f(s.flags)));
+    sts(&p.b.pTLPI[4u * (size_t)slot + 0u], make_float4(s.T.x, s.T.y, s.T.z, s.last_pdf));
+    sts(&p.b.pTLPI[4u * (size_t)slot + 1u], make_float4(s.L.x, s.L.y, s.L.z, u_as_f(s.rng)));
+    sts(&p.b.pTLPI[4u * (size_t)slot + 2u], make_float4(s.pending.x, s.pending.y, s.pending.z, u_as_f(s.flags)));
 }
 
 // shader.wgsl:1249-1264: the last next-event sample counts iff nothing blocked its ray.
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(kShadeThreads, RT_WAVE_SHADE_MIN_BLOCKS) wave_
             PathRegs s;
             load_path(p, slot, s);
             settle_shadow(p, slot, s);
-            uint4 I = lds((const uint4*)&p.b.pPI[2u * (size_t)slot + 1u]);
+            uint4 I = lds((const uint4*)&p.b.pTLPI[4u * (size_t)slot + 3u]);
             const float4 o4 = lds(&p.b.rOD[2u * (size_t)slot + 0u]), d4 = lds(&p.b.rOD[2u * (size_t)slot + 1u]), h4 = lds(&p.b.hit[slot]);
             FHit hit;
             hit.t = h4.x;
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(kShadeThreads, RT_WAVE_SHADE_MIN_BLOCKS) wave_
                 p.b.stage[slot] = STAGE_FLIGHT;
                 n_rays++;
             }
-            sts((uint4*)&p.b.pPI[2u * (size_t)slot + 1u], I);
+            sts((uint4*)&p.b.pTLPI[4u * (size_t)slot + 3u], I);
             store_path(p, slot, s);
         }
         list_push2(rayq, &c->ray_n[P], emit_closest, slot, emit_shadow, slot | kShadowBit);
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wav
         PathRegs s;
         s.rng = 0u;
         if (on) {
-            I = lds((const uint4*)&p.b.pPI[2u * (size_t)slot + 1u]);
+            I = lds((const uint4*)&p.b.pTLPI[4u * (size_t)slot + 3u]);
             if (I.w != SLOT_NEW) {
                 load_path(p, slot, s);
                 settle_shadow(p, slot, s);
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wav
                 n_paths++;
                 n_rays++;
             }
-            sts((uint4*)&p.b.pPI[2u * (size_t)slot + 1u], I);
+            sts((uint4*)&p.b.pTLPI[4u * (size_t)slot + 3u], I);
         }
         list_push(rayq, &c->ray_n[P], emit, slot);
         const unsigned gone = __ballot_sync(0xFFFFFFFFu, retire);
