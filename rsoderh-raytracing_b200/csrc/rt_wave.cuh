@@ -184,6 +184,7 @@ struct PathRegs {
     V3 T, L, pending;
     float last_pdf;
     uint32_t rng, flags;
+    uint32_t occluded;  // the slot's occlusion byte, fetched with the rest (no dependent load)
 };
 
 RT_DEVONLY void load_path(const WaveParams& p, uint32_t slot, PathRegs& s) {
@@ -194,6 +195,7 @@ RT_DEVONLY void load_path(const WaveParams& p, uint32_t slot, PathRegs& s) {
     s.rng = f_as_u(l4.w);
     s.pending = xyz(p4);
     s.flags = f_as_u(p4.w);
+    s.occluded = p.b.occl[slot];
 }
 
 RT_DEVONLY void store_path(const WaveParams& p, uint32_t slot, const PathRegs& s) {
@@ -204,7 +206,7 @@ RT_DEVONLY void store_path(const WaveParams& p, uint32_t slot, const PathRegs& s
 
 // shader.wgsl:1249-1264: the last next-event sample counts iff nothing blocked its ray.
 RT_DEVONLY void settle_shadow(const WaveParams& p, uint32_t slot, PathRegs& s) {
-    if ((s.flags & kFlagShadow) && p.b.occl[slot] == 0) s.L = s.L + s.pending;
+    if ((s.flags & kFlagShadow) && s.occluded == 0u) s.L = s.L + s.pending;
     s.flags = 0u;
 }
 
@@ -214,7 +216,9 @@ RT_DEVONLY void settle_shadow(const WaveParams& p, uint32_t slot, PathRegs& s) {
 
 // Sweeps `stage` in slot order; `body(slot, on)` runs with up to 32 compacted slots per
 // warp call (on == false for lanes without one). Leftovers are carried to the next chunk so
-// the lanes stay full; every lane of the warp reaches every body call.
+// the lanes stay full; every lane of the warp reaches every body call. The body has ONE call
+// site (the last, partial batch goes through the same loop): inlined twice it doubled the
+// kernel's footprint in the instruction cache.
 template <int THREADS, typename Body>
 RT_DEVONLY void sweep_stage(const WaveParams& p, uint8_t want, uint8_t convert_from, uint8_t convert_to,
                             Body&& body) {
@@ -224,25 +228,40 @@ RT_DEVONLY void sweep_stage(const WaveParams& p, uint8_t want, uint8_t convert_f
     const uint32_t warps = gridDim.x * (THREADS / 32);
     const uint32_t chunks = (p.slots + 31u) / 32u;
     uint32_t n = 0;
-    for (uint32_t chunk = blockIdx.x * (THREADS / 32) + warp; chunk < chunks; chunk += warps) {
+    // The stage bytes of the next chunk are requested before the current chunk is worked on, so
+    // the sweep does not wait a memory latency per chunk.
+    auto load_stage = [&](uint32_t chunk) -> uint8_t {
         const uint32_t slot = chunk * 32u + lane;
-        uint8_t st = slot < p.slots ? p.b.stage[slot] : (uint8_t)STAGE_IDLE;
-        if (convert_from && st == convert_from) p.b.stage[slot] = convert_to;
-        const bool need = st == want;
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, need);
-        if (need) list[n + __popc(m & ((1u << lane) - 1u))] = slot;
-        n += __popc(m);
-        __syncwarp();
-        if (n >= 32u) {
-            body(list[lane], true);
-            n -= 32u;
+        return (chunk < chunks && slot < p.slots) ? p.b.stage[slot] : (uint8_t)STAGE_IDLE;
+    };
+    uint32_t chunk = blockIdx.x * (THREADS / 32) + warp;
+    uint8_t st_next = load_stage(chunk);
+    for (;;) {
+        const bool more = chunk < chunks;
+        if (more) {
+            const uint32_t slot = chunk * 32u + lane;
+            const uint8_t st = st_next;
+            chunk += warps;
+            st_next = load_stage(chunk);
+            if (convert_from && st == convert_from) p.b.stage[slot] = convert_to;
+            const bool need = st == want;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, need);
+            if (need) list[n + __popc(m & ((1u << lane) - 1u))] = slot;
+            n += __popc(m);
+            __syncwarp();
+        }
+        if (n >= 32u || (!more && n > 0u)) {
+            const uint32_t take = n < 32u ? n : 32u;
+            body(lane < take ? list[lane] : 0u, lane < take);
+            n -= take;
             const uint32_t carry = lane < n ? list[32u + lane] : 0u;
             __syncwarp();
             if (lane < n) list[lane] = carry;
             __syncwarp();
+        } else if (!more) {
+            break;
         }
     }
-    if (n > 0u) body(lane < n ? list[lane] : 0u, lane < n);
 }
 
 // Slots whose ray hit something: shade, emit the next rays.
@@ -319,26 +338,15 @@ __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wav
         uint4 I = make_uint4(0u, 0u, 0u, SLOT_RETIRED);
         PathRegs s;
         s.rng = 0u;
+        float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (on) {
+            // Everything the slot may need is requested at once (no load waits on another);
+            // a new slot's record is uninitialised and ignored.
             I = lds((const uint4*)&p.b.pTLPI[4u * (size_t)slot + 3u]);
-            if (I.w != SLOT_NEW) {
-                load_path(p, slot, s);
-                settle_shadow(p, slot, s);
-                if (I.w == SLOT_TRACED) {
-                    // shader.wgsl:1222-1231 — the ray escaped into the environment.
-                    const V3 d = xyz(lds(&p.b.rOD[2u * (size_t)slot + 1u]));
-                    float u, v;
-                    direction_to_uv(d, u, v);
-                    V3 sky = env_bilinear(p.env, u, v);
-                    float pdf = env_direction_pdf(p.env, u, v);
-                    float w = power_heuristic(s.last_pdf, pdf);
-                    s.L = s.L + s.T * sky * w;
-                }
-                // Park the sample; wave_accumulate_kernel adds the planes in sample order.
-                p.staging[(size_t)(I.y - p.batch_begin) * pixels + I.x] = make_float4(s.L.x, s.L.y, s.L.z, 0.0f);
-            }
+            load_path(p, slot, s);
+            d4 = lds(&p.b.rOD[2u * (size_t)slot + 1u]);
         }
-        // ---- hand out the next path indices: one atomic per warp ----
+        // ---- hand out the next path indices: one atomic per warp, in flight during the sky lookup ----
         uint32_t q = kNone;
         {
             const unsigned m = __ballot_sync(0xFFFFFFFFu, on);
@@ -350,6 +358,21 @@ __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wav
                 base = __shfl_sync(0xFFFFFFFFu, base, leader);
                 if (on) q = base + __popc(m & ((1u << lane) - 1u));
             }
+        }
+        if (on && I.w != SLOT_NEW) {
+            settle_shadow(p, slot, s);
+            if (I.w == SLOT_TRACED) {
+                // shader.wgsl:1222-1231 — the ray escaped into the environment.
+                const V3 d = xyz(d4);
+                float u, v;
+                direction_to_uv(d, u, v);
+                V3 sky = env_bilinear(p.env, u, v);
+                float pdf = env_direction_pdf(p.env, u, v);
+                float w = power_heuristic(s.last_pdf, pdf);
+                s.L = s.L + s.T * sky * w;
+            }
+            // Park the sample; wave_accumulate_kernel adds the planes in sample order.
+            p.staging[(size_t)(I.y - p.batch_begin) * pixels + I.x] = make_float4(s.L.x, s.L.y, s.L.z, 0.0f);
         }
         if (on) {
             uint32_t px = 0, py = 0;
