@@ -459,14 +459,6 @@ RT_DEVONLY void fast_flush_counts(uint32_t paths, uint32_t rays, uint32_t shadow
 #define RT_FAST_MIN_BLOCKS 5
 #endif
 
-#ifndef RT_FAST_SYNC
-#define RT_FAST_SYNC 0
-#endif
-#if defined(RT_SHADE_NOINLINE) && RT_SHADE_NOINLINE
-#define RT_SHADE_QUAL __device__ __noinline__
-#else
-#define RT_SHADE_QUAL RT_DEVONLY
-#endif
 
 // What a shaded hit hands back to the path loop.
 struct ShadeOut {
@@ -480,7 +472,7 @@ struct ShadeOut {
 
 // shader.wgsl:1233-1298 for one closest hit: emission, next-event estimation set-up,
 // bsdf_sample and the throughput update. L and T are updated in place.
-RT_SHADE_QUAL void shade_hit(const FastScene& sc, const EnvView& env, V3 o, V3 d, const FHit& hit, uint32_t& rng,
+RT_DEVONLY void shade_hit(const FastScene& sc, const EnvView& env, V3 o, V3 d, const FHit& hit, uint32_t& rng,
                              V3& T, V3& L, ShadeOut& out) {
     V3 n;
     uint32_t mat_id;
@@ -621,11 +613,7 @@ __global__ void __launch_bounds__(kFastThreads, RT_FAST_MIN_BLOCKS) render_fast_
     float last_pdf = 1.0f;
     bool fresh = true;  // the lane needs a camera ray
 
-#if RT_FAST_SYNC
-    while (__syncthreads_or(sample < sample_end)) {
-#else
     while (sample < sample_end) {
-#endif
         const bool alive = sample < sample_end;
         if (alive && fresh) {
             camera_ray(p.camera, sin_half_fov, px, py, p.width, p.height, sample, rng, o, d);
