@@ -407,7 +407,7 @@ struct RtContext {
     int wave_groups = 2;
     int wave_blocks1[4] = {RT_WAVE_SHADE_MIN_BLOCKS, RT_WAVE_FINISH_MIN_BLOCKS, RT_WAVE_PREPASS_MIN_BLOCKS,
                            RT_WAVE_WALK_MIN_BLOCKS};  // blocks per SM of shade, finish, pre-pass, walk: one group
-    int wave_blocks2[4] = {8, 8, 4, 4};               // ... two groups (measured best: full grids on both streams)
+    int wave_blocks2[4] = {8, 8, 4, 5};               // ... two groups (measured best: full grids on both streams)
     void* wave_staging = nullptr;     // per-sample radiance planes of the current batch
     size_t wave_staging_bytes = 0;
     size_t wave_staging_budget = (size_t)8192 << 20;

@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(kPrepassThreads, RT_WAVE_PREPASS_MIN_BLOCKS) w
 }
 
 #ifndef RT_WAVE_WALK_MIN_BLOCKS
-#define RT_WAVE_WALK_MIN_BLOCKS 4
+#define RT_WAVE_WALK_MIN_BLOCKS 5
 #endif
 
 // The triangle walk of every queued ray. Persistent warps; a lane whose ray is finished
