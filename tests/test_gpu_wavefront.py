@@ -134,3 +134,47 @@ def test_profile_reports_every_kernel(rt, house, env_small):
         assert k["launches"] == prof["waves"] and k["ms"] > 0, name
     assert sum(k["ms"] for k in prof["kernels"].values()) <= prof["total_ms"] * 1.05
     assert st.launch_count() >= 4 * prof["waves"]
+
+
+def test_tiny_scenes_through_the_pipeline(rt, orc, env_small):
+    # Scenes whose BVH root is a leaf, or whose effective tree is empty (spheres / planes only,
+    # all hoisted): every ray is settled by the pre-pass kernel.
+    builders = [lambda b: b.add_sphere((0, 0, 0), 1.0, 0),
+                lambda b: b.add_plane((-1, 0, -1), (0, 0, 2), (2, 0, 0), 0).add_sphere((0, 1, 0), 0.5, 0),
+                lambda b: b.add_mesh_raw([[0, 0, 0], [1, 0, 0], [0, 1, 0]], [[0, 0, 1]], [[0, 1, 2, 0, 0, 0]], 0)]
+    for build in builders:
+        b = rt.SceneBuilder().add_material((0.8, 0.7, 0.6), 0.4, 0.0)
+        scene = build(b).set_camera((0.2, 0.4, 3), 0.0, 0.0, 1.0).build()
+        w, h = 96, 64
+        st, got = _render(rt, scene, env_small, w, h, 3, 6)
+        ora = orc.Oracle(scene, env_small, w, h, max_bounces=6)
+        want, _ = ora.render(0, 3)
+        assert got.tobytes() == want.tobytes(), _report(got, want)
+        slots, t = st.first_hit(0)
+        oslots, ot, _ = ora.first_hit(0)
+        assert np.array_equal(slots, oslots) and t.tobytes() == ot.tobytes()
+
+
+def test_degenerate_big_leaf_on_gpu(rt, orc, env_small):
+    # 40 triangles whose boxes share one centre cannot be split (bvh.rs:238-244): a leaf longer
+    # than the inline length field of the N2 records, next to ordinary geometry.
+    rng = np.random.default_rng(9)
+    verts, tris = [], []
+    for _ in range(40):
+        a = np.round(rng.uniform(0.5, 2.0, size=3) * rng.choice([-1, 1], size=3) * 8) / 8
+        base = len(verts)
+        verts += [a, -a, a * np.array([0.5, -0.5, 0.25])]
+        tris.append([base, base + 1, base + 2, 0, 0, 0])
+    b = rt.SceneBuilder().add_material((0.8, 0.8, 0.8), 1.0, 0.0)
+    b.add_mesh_raw(np.array(verts), [[0, 0, 1]], tris, 0).add_mesh_obj(_cube_at((4, 0, 0)), 0)
+    b.add_sphere((-4, 0, 0), 1.0, 0)
+    scene = b.set_camera((0, 0, 7), 0.0, 0.0, 1.0).build()
+    assert scene.bvh_nodes_words()[:, 9].max() >= 31
+    w, h = 160, 90
+    st, got = _render(rt, scene, env_small, w, h, 2, 4)
+    ora = orc.Oracle(scene, env_small, w, h, max_bounces=4)
+    want, _ = ora.render(0, 2)
+    assert got.tobytes() == want.tobytes(), _report(got, want)
+    slots, t = st.first_hit(0)
+    oslots, ot, _ = ora.first_hit(0)
+    assert np.array_equal(slots, oslots) and t.tobytes() == ot.tobytes()
