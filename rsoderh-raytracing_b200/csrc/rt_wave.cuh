@@ -9,8 +9,9 @@
 //   wave_shade_kernel    slots whose ray hit -> settle last shadow ray, shade (emission,
 //                        next-event set-up, BSDF sample), emit the bounce ray + shadow ray
 //   wave_finish_kernel   slots whose path is over / ray escaped / are new -> settle, sky light,
-//                        accumulate the sample, start the pixel's next one (camera ray)
-//   wave_prepass_kernel  ray queue -> the analytic pre-pass (rt_fast.cuh) of every emitted ray
+//                        park the finished sample, take the next path (camera ray)
+//   wave_prepass_kernel  ray queue -> the analytic pre-pass (rt_fast.cuh) of every emitted ray;
+//                        rays with no triangle to test are finished here and leave the queue
 //   wave_walk_kernel     ray queue -> the triangle walk alone (a few KB of code): persistent
 //                        warps whose lanes pull the next ray the moment their own is finished
 // shade and finish find their slots by sweeping a one-byte stage array in slot order and
@@ -19,7 +20,7 @@
 // The bounce ray and the shadow ray of one hit do not depend on each other and travel in
 // the same wave. The slots are split into two groups whose waves run half a wave apart on
 // two streams, so one group's memory-bound shade / finish overlaps the other's issue-bound
-// pre-pass / walk. Path state lives in global memory (~170 B per slot).
+// pre-pass / walk. Path state lives in global memory (~162 B per slot).
 //
 // Paths are independent work items: a slot that finishes a path takes the next path index
 // from a global counter (sample-major, pixels in 8x8-tile order inside a sample), so the
@@ -43,7 +44,7 @@ constexpr int kFinishThreads = 128;
 constexpr int kPrepassThreads = 256;
 constexpr int kWalkThreads = 256;
 
-// pI.w of a slot
+// state word of a slot (pTLPI[4 * slot + 3].w)
 enum SlotState : uint32_t {
     SLOT_RETIRED = 0,
     SLOT_NEW = 1,     // needs its first camera ray
@@ -72,9 +73,10 @@ struct WaveCtrl {
 };
 
 struct WaveBuffers {
-    // Arrays of 32-byte pairs: vectors that are always used together share a DRAM sector, so
-    // the scattered slots a warp works on waste no half sectors. (One 128-byte record per
-    // slot measured slower: the pre-pass and the walk touch only the ray vectors.)
+    // Vectors that are always used together are neighbours in memory (a 32-byte ray pair, a
+    // 64-byte path record), so the scattered slots a warp works on waste no half sectors.
+    // (One record per slot holding everything, 128 or 64 + 64 bytes, measured slower: the
+    // pre-pass and the walk touch only the ray vectors.)
     float4* rOD;      // [S][2] ray origin (.w = closest analytic distance from the pre-pass),
                       //        direction of the closest-hit ray (.w = bits rec of that analytic hit)
     float4* sray_d;   // [S] direction of the shadow ray
