@@ -92,6 +92,8 @@ int rt_render(RtContext* ctx, uint32_t sample_begin, uint32_t sample_count, uint
  * brute-force fallback (shader.wgsl:583-598). t_out (optional) = hit distance, 0 on miss.
  * Host output buffers; synchronous. */
 int rt_first_hit(RtContext* ctx, uint32_t sample_index, uint32_t* slot_out, float* t_out);
+/* Device time (CUDA events) of the kernel of the last rt_first_hit call, without its copies. */
+float rt_first_hit_kernel_ms(const RtContext* ctx);
 
 int rt_sync(RtContext* ctx);
 /* Device -> host copy of the W*H*4 accumulation floats (alpha = 1 where rendered). */

@@ -163,6 +163,7 @@ BACKEND_SIGNATURES = {
     "rt_clear": (C.c_int, [_vp]),
     "rt_render": (C.c_int, [_vp, _u32, _u32, _u32, _u32]),
     "rt_first_hit": (C.c_int, [_vp, _u32, _vp, _vp]),
+    "rt_first_hit_kernel_ms": (C.c_float, [_vp]),
     "rt_sync": (C.c_int, [_vp]),
     "rt_read_accum": (C.c_int, [_vp, _vp]),
     "rt_write_accum": (C.c_int, [_vp, _vp]),

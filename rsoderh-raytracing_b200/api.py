@@ -414,6 +414,10 @@ class State:
         self._check(self._lib.rt_first_hit(self._ctx, sample_index, slots.ctypes.data, t.ctypes.data))
         return slots, t
 
+    def first_hit_kernel_ms(self) -> float:
+        """Device time of the last first_hit() kernel, without its device-to-host copies."""
+        return float(self._lib.rt_first_hit_kernel_ms(self._ctx))
+
     def tonemap_rgb8(self, sample_total: Optional[int] = None) -> np.ndarray:
         out = np.empty((self.height, self.width, 3), dtype=np.uint8)
         total = self.sample_count if sample_total is None else sample_total

@@ -418,6 +418,7 @@ struct RtContext {
     bool profiling = false;
     RtWaveProfile profile{};
     bool detailed = false;
+    float first_hit_kernel_ms = 0.f;  // device time of the last rt_first_hit kernel
     uint64_t launches = 0;
 };
 
@@ -1286,6 +1287,7 @@ int rt_first_hit(RtContext* ctx, uint32_t sample_index, uint32_t* slot_out, floa
     p.width = ctx->width;
     p.height = ctx->height;
     p.sample = sample_index;
+    cudaEventRecord(ctx->ev_start, ctx->stream);
     if ((ctx->kernel == RtContext::KERNEL_FAST || ctx->kernel == RtContext::KERNEL_WAVE) && !ctx->detailed) {
         rtf::FastParams fp;
         memset(&fp, 0, sizeof fp);
@@ -1307,11 +1309,13 @@ int rt_first_hit(RtContext* ctx, uint32_t sample_index, uint32_t* slot_out, floa
                           : launch_first_hit<false>(p, ctx->bvh_depth, ctx->stream);
     }
     ctx->launches++;
+    cudaEventRecord(ctx->ev_stop, ctx->stream);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(slot_out, d_slot, count * 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && t_out)
         e = cudaMemcpyAsync(t_out, d_t, count * 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) cudaEventElapsedTime(&ctx->first_hit_kernel_ms, ctx->ev_start, ctx->ev_stop);
     cudaFree(d_slot);
     cudaFree(d_t);
     if (e != cudaSuccess)
@@ -1439,6 +1443,8 @@ int rt_timer_stop(RtContext* ctx, float* elapsed_ms) {
 }
 
 uint64_t rt_launch_count(const RtContext* ctx) { return ctx ? ctx->launches : 0; }
+
+float rt_first_hit_kernel_ms(const RtContext* ctx) { return ctx ? ctx->first_hit_kernel_ms : 0.f; }
 
 }  // extern "C"
 
