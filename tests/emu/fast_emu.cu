@@ -49,6 +49,86 @@ void emu_scene_free(void* h) { delete (EmuScene*)h; }
 
 int emu_scene_hoisted(void* h) { return (int)((EmuScene*)h)->layout.view.hoisted; }
 
+// Structural check of the effective tree: walks every N2 record from the root and verifies
+// that each interior box encloses its children's boxes, that leaf refs are well formed and
+// that every triangle slot is covered exactly once. out = {interior records, walked leaves,
+// triangle slots covered, max depth, pre-pass leaves, boxes, prims, hoisted}. Returns 0 when
+// consistent, otherwise a code naming the first violated property.
+int emu_check_layout(void* h, const RtSceneDesc* s, uint32_t out[8]) {
+    using namespace rtf;
+    EmuScene* e = (EmuScene*)h;
+    const FastScene& sc = e->layout.view;
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    out[4] = sc.pre_leaves;
+    out[5] = sc.pre_boxes;
+    out[6] = sc.pre_prims;
+    out[7] = sc.hoisted;
+    std::vector<uint8_t> seen(s->primitive_count, 0);
+    struct Item {
+        uint32_t ref, depth;
+        float mn[3], mx[3];
+    };
+    std::vector<Item> todo;
+    if (sc.root_ref != kNone) {
+        Item r;
+        r.ref = sc.root_ref;
+        r.depth = 0;
+        for (int a = 0; a < 3; a++) {
+            r.mn[a] = sc.root_min[a];
+            r.mx[a] = sc.root_max[a];
+        }
+        todo.push_back(r);
+    }
+    while (!todo.empty()) {
+        Item it = todo.back();
+        todo.pop_back();
+        if (it.depth > out[3]) out[3] = it.depth;
+        if (it.ref & kLeafBit) {
+            const uint32_t first = it.ref & kLeafSlotMask;
+            uint32_t len = (it.ref >> kLeafLenShift) & 31u;
+            if (len == kLeafLenEscape) {
+                if (!sc.big_len) return 1;
+                len = sc.big_len[first];
+            }
+            if (len == 0 || (uint64_t)first + len > s->primitive_count) return 2;
+            out[1]++;
+            for (uint32_t k = first; k < first + len; k++) {
+                if (seen[k]) return 3;  // a slot reachable twice
+                seen[k] = 1;
+                if (s->primitives[k].primitive_type == 2u) out[2]++;
+            }
+            continue;
+        }
+        if ((size_t)it.ref * 4 + 3 >= e->layout.n2.size()) return 4;
+        out[0]++;
+        const float4* q = sc.n2 + 4u * (size_t)it.ref;
+        const float4 boxes[2][2] = {{q[0], q[1]}, {q[2], q[3]}};
+        const uint32_t refs[2] = {rtd::f_as_u(q[0].w), rtd::f_as_u(q[1].w)};
+        if (rtd::f_as_u(q[3].w) > 2u) return 5;  // split axis
+        for (int c = 0; c < 2; c++) {
+            if (refs[c] == kNone) return 6;  // the effective tree has no empty children
+            Item ch;
+            ch.ref = refs[c];
+            ch.depth = it.depth + 1;
+            const float mn[3] = {boxes[c][0].x, boxes[c][0].y, boxes[c][0].z};
+            const float mx[3] = {boxes[c][1].x, boxes[c][1].y, boxes[c][1].z};
+            for (int a = 0; a < 3; a++) {
+                if (mn[a] < it.mn[a] || mx[a] > it.mx[a]) return 7;  // child sticks out of its parent
+                ch.mn[a] = mn[a];
+                ch.mx[a] = mx[a];
+            }
+            todo.push_back(ch);
+        }
+    }
+    // every triangle must be walked; analytic primitives are walked iff not hoisted
+    for (uint32_t k = 0; k < s->primitive_count; k++) {
+        const bool tri = s->primitives[k].primitive_type == 2u;
+        if (tri && !seen[k]) return 8;
+        if (!tri && !sc.hoisted && !seen[k]) return 9;
+    }
+    return 0;
+}
+
 // Traces n rays (origins/directions are xyz triples). code_out uses rt_first_hit's encoding
 // (slot, fallback code or RT_MISS_SLOT); for any_hit rays only "hit or not" is meaningful.
 void emu_trace(void* h, uint32_t n, const float* origins, const float* dirs, int any_hit,

@@ -35,6 +35,8 @@ def emu():
     lib.emu_scene_hoisted.argtypes = [C.c_void_p]
     lib.emu_trace.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                               C.c_void_p, C.c_void_p]
+    lib.emu_check_layout.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32 * 8)]
+    lib.emu_check_layout.restype = C.c_int
     return lib
 
 
@@ -45,6 +47,13 @@ class Emu:
 
     def __del__(self):
         self.lib.emu_scene_free(self.h)
+
+    def check_layout(self):
+        """(status, stats) of the structural check of the effective tree."""
+        out = (C.c_uint32 * 8)()
+        st = self.lib.emu_check_layout(self.h, C.addressof(self.scene.desc), C.byref(out))
+        keys = ("interior", "leaves", "triangles", "depth", "pre_leaves", "pre_boxes", "pre_prims", "hoisted")
+        return st, dict(zip(keys, list(out)))
 
     @property
     def hoisted(self):
@@ -239,3 +248,25 @@ def test_degenerate_big_leaf(rt, orc, emu, env_small):
     es = Emu(emu, scene)
     ora = orc.Oracle(scene, env_small, 64, 36)
     _exercise(es, ora, rng, (-6, -3, -3), (6, 3, 3), n=20000)
+
+
+def test_effective_tree_structure(rt, emu):
+    # The tree the walk uses: every triangle slot covered exactly once, children inside their
+    # parents' (tight) boxes, no empty children; hoisted leaves are gone and single-child
+    # nodes spliced out, so it has fewer interior records than the reference's tree.
+    cases = {"house": (52, 39), "default": (12, 15), "suzanne": (968, 545)}
+    for name, (tris, ref_nodes) in cases.items():
+        scene = rt.Scene.load_toml(os.path.join(ASSETS, "scenes", f"{name}.toml"))
+        st, stats = Emu(emu, scene).check_layout()
+        assert st == 0, (name, st, stats)
+        assert stats["triangles"] == tris and stats["hoisted"] == 1
+        ref_interior = (ref_nodes - 1) // 2
+        assert stats["interior"] == stats["leaves"] - 1 <= ref_interior
+        if name != "suzanne":
+            assert stats["interior"] < ref_interior and stats["pre_prims"] > 0
+    # house: two analytic leaves (planes, spheres), the duplicate ground plane dropped
+    st, stats = Emu(emu, rt.Scene.load_toml(os.path.join(ASSETS, "scenes", "house.toml"))).check_layout()
+    assert (stats["pre_leaves"], stats["pre_prims"]) == (2, 3)
+    field = rt.Scene.synthetic_field(ASSETS, 6)
+    st, stats = Emu(emu, field).check_layout()
+    assert st == 0 and stats["triangles"] == field.counts()["triangles"] and stats["depth"] <= field.bvh_depth
