@@ -101,12 +101,14 @@ struct RayCtx {
 
 // ray_intersects_bounds (shader.wgsl:262-293) with the far bound starting at `limit`.
 // Returns the entry distance t0 through `t0_out`.
+// ASSUME_PLAIN: the caller knows r.plain holds for every lane (no branch on it).
+template <bool ASSUME_PLAIN = false>
 RT_DEV bool box_test(const RayCtx& r, float4 bmin, float4 bmax, float limit, float& t0_out) {
     float tnx = (bmin.x - r.o.x) * r.inv.x, tfx = (bmax.x - r.o.x) * r.inv.x;
     float tny = (bmin.y - r.o.y) * r.inv.y, tfy = (bmax.y - r.o.y) * r.inv.y;
     float tnz = (bmin.z - r.o.z) * r.inv.z, tfz = (bmax.z - r.o.z) * r.inv.z;
     float t0, t1;
-    if (r.plain) {
+    if (ASSUME_PLAIN || r.plain) {
         t0 = fmaxf(fmaxf(0.0f, fminf(tnx, tfx)), fmaxf(fminf(tny, tfy), fminf(tnz, tfz)));
         t1 = fminf(fminf(limit, fmaxf(tnx, tfx)), fminf(fmaxf(tny, tfy), fmaxf(tnz, tfz)));
     } else {
@@ -302,14 +304,15 @@ RT_DEV void walk_pop(Walk& w, const uint2* stack) {
 }
 
 // One interior record: both children's boxes, near child next, far child pushed.
+template <bool ASSUME_PLAIN = false>
 RT_DEV void walk_node(const FastScene& sc, const RayCtx& r, Walk& w, uint2* stack) {
     const float4* q = sc.n2 + 4u * (size_t)w.cur;
     const float4 q0 = ld4(q), q1 = ld4(q + 1), q2 = ld4(q + 2), q3 = ld4(q + 3);
     float t0a, t0b;
     // A missed child is marked by an entry distance no hit can have (t0 <= limit < inf).
     const float kMiss = __builtin_huge_valf();
-    if (!box_test(r, q0, q1, w.limit, t0a)) t0a = kMiss;
-    if (!box_test(r, q2, q3, w.limit, t0b)) t0b = kMiss;
+    if (!box_test<ASSUME_PLAIN>(r, q0, q1, w.limit, t0a)) t0a = kMiss;
+    if (!box_test<ASSUME_PLAIN>(r, q2, q3, w.limit, t0b)) t0b = kMiss;
     const bool second_first = ((r.neg >> f_as_u(q3.w)) & 1u) != 0u;  // shader.wgsl:536
     const uint32_t rn = second_first ? f_as_u(q1.w) : f_as_u(q0.w);
     const uint32_t rf = second_first ? f_as_u(q0.w) : f_as_u(q1.w);

@@ -535,7 +535,13 @@ __global__ void __launch_bounds__(kWalkThreads, RT_WAVE_WALK_MIN_BLOCKS) wave_wa
         }
 
         // ---- one round of the walk: interior records, then the leaf ----
-        while (busy && w.cur < kLeafBit) walk_node(p.scene, r, w, stack);
+        // Rays with an infinite 1/d component are rare (axis-aligned directions): when the warp
+        // holds none, the box tests skip the NaN-safe form without a branch.
+        if (__all_sync(0xFFFFFFFFu, !busy || r.plain)) {
+            while (busy && w.cur < kLeafBit) walk_node<true>(p.scene, r, w, stack);
+        } else {
+            while (busy && w.cur < kLeafBit) walk_node<false>(p.scene, r, w, stack);
+        }
         bool settled = false;
         if (busy && w.cur != kNone) settled = walk_leaf(p.scene, r, any_hit, best, w, stack);
 
