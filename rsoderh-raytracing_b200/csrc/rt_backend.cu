@@ -398,7 +398,8 @@ struct RtContext {
     enum Kernel { KERNEL_WAVE, KERNEL_FAST, KERNEL_PIXEL };
     Kernel kernel = KERNEL_WAVE;
     // wavefront pipeline state (rt_wave.cuh)
-    rtw::WaveBuffers wave[2]{};
+    static constexpr int kMaxGroups = 4;
+    rtw::WaveBuffers wave[kMaxGroups]{};
     void* wave_arena = nullptr;
     uint32_t wave_slots = 0;          // per-group capacity the arena was allocated for
     int wave_arena_groups = 0;
@@ -411,10 +412,10 @@ struct RtContext {
     void* wave_staging = nullptr;     // per-sample radiance planes of the current batch
     size_t wave_staging_bytes = 0;
     size_t wave_staging_budget = (size_t)8192 << 20;
-    uint32_t* wave_live_host = nullptr;  // pinned read-back of WaveCtrl::live: [2 chunks in flight][2 groups]
-    cudaStream_t wave_streams[2] = {nullptr, nullptr};
-    cudaEvent_t wave_events[2][2] = {};
-    cudaEvent_t wave_fork = nullptr, wave_phase = nullptr, wave_join[2] = {nullptr, nullptr};
+    uint32_t* wave_live_host = nullptr;  // pinned read-back of WaveCtrl::live: [2 chunks in flight][groups]
+    cudaStream_t wave_streams[kMaxGroups] = {};
+    cudaEvent_t wave_events[2][kMaxGroups] = {};
+    cudaEvent_t wave_fork = nullptr, wave_phase[kMaxGroups] = {}, wave_join[kMaxGroups] = {};
     bool profiling = false;
     RtWaveProfile profile{};
     bool detailed = false;
@@ -595,12 +596,12 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
     if (batch < 1) batch = 1;
     const uint64_t paths_per_batch = (uint64_t)base.pixel_ids * batch;
     const uint32_t total_slots = (uint32_t)(paths_per_batch < ctx->wave_max_slots ? paths_per_batch : ctx->wave_max_slots);
-    const int groups = (ctx->wave_groups >= 2 && total_slots >= 262144u) ? 2 : 1;  // small frames: one group
+    const int groups = total_slots >= 262144u ? ctx->wave_groups : 1;  // small frames: one group
     const uint32_t per_group = (total_slots + (uint32_t)groups - 1u) / (uint32_t)groups;
     int st = wave_reserve(ctx, per_group, groups, pixels * sizeof(float4) * (size_t)batch);
     if (st != RT_OK) return st;
 
-    rtw::WaveParams p[2];
+    rtw::WaveParams p[RtContext::kMaxGroups];
     for (int g = 0; g < groups; g++) {
         p[g] = base;
         p[g].b = ctx->wave[g];
@@ -615,7 +616,7 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
     };
     // Blocks per SM are tunable per group count (RT_WAVE_BLOCKS2); full-size grids on both
     // streams measured best, the block scheduler interleaves the two kernels as SMs free up.
-    const int* per_sm = groups == 2 ? ctx->wave_blocks2 : ctx->wave_blocks1;
+    const int* per_sm = groups >= 2 ? ctx->wave_blocks2 : ctx->wave_blocks1;
     const unsigned shade_blocks = blocks_for(per_group, rtw::kShadeThreads, per_sm[0]);
     const unsigned finish_blocks = blocks_for(per_group, rtw::kFinishThreads, per_sm[1]);
     const unsigned prepass_blocks = blocks_for(2u * per_group, rtw::kPrepassThreads, per_sm[2]);
@@ -624,7 +625,7 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
     // RT_WAVE_TIMELINE=1 (diagnostics) or rt_set_profiling: CUDA events around every kernel.
     static const bool timeline_print = getenv("RT_WAVE_TIMELINE") != nullptr;
     const bool timeline = timeline_print || ctx->profiling;
-    std::vector<cudaEvent_t> tl[2];
+    std::vector<cudaEvent_t> tl[RtContext::kMaxGroups];
     auto mark = [&](int g, cudaStream_t s) {
         if (!timeline) return;
         cudaEvent_t ev;
@@ -634,7 +635,7 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
     };
     // One wave of group g: kernels first .. last-1 of (shade, finish, pre-pass, walk).
     auto launch = [&](int g, uint32_t wave, int first, int last) {
-        cudaStream_t s = groups == 2 ? ctx->wave_streams[g] : ctx->stream;
+        cudaStream_t s = groups >= 2 ? ctx->wave_streams[g] : ctx->stream;
         p[g].wave = wave;
         for (int k = first; k < last; k++) {
             mark(g, s);
@@ -661,13 +662,13 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
             p[g].path_total = base.pixel_ids * p[g].batch_count;
         }
         cudaMemsetAsync(ctx->wave_next_path, 0, sizeof(uint32_t), ctx->stream);
-        if (groups == 2) {
-            // fork: both group streams start after everything queued on the context's stream
+        if (groups >= 2) {
+            // fork: the group streams start after everything queued on the context's stream
             cudaEventRecord(ctx->wave_fork, ctx->stream);
-            for (int g = 0; g < 2; g++) cudaStreamWaitEvent(ctx->wave_streams[g], ctx->wave_fork, 0);
+            for (int g = 0; g < groups; g++) cudaStreamWaitEvent(ctx->wave_streams[g], ctx->wave_fork, 0);
         }
         for (int g = 0; g < groups; g++) {
-            cudaStream_t s = groups == 2 ? ctx->wave_streams[g] : ctx->stream;
+            cudaStream_t s = groups >= 2 ? ctx->wave_streams[g] : ctx->stream;
             rtw::wave_init_kernel<<<(per_group + 255) / 256, 256, 0, s>>>(p[g]);
             ctx->launches++;
         }
@@ -676,26 +677,25 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
         uint32_t wave = 0;
         for (uint32_t k = 0;; k++) {
             for (uint32_t i = 0; i < chunk; i++, wave++) {
-                if (groups == 1) {
-                    launch(0, wave, 0, 4);
-                } else if (wave == 0) {
-                    // Group 1 starts half a wave late: its shade + finish run beside group 0's
-                    // pre-pass + walk from then on.
-                    launch(0, 0, 0, 2);
-                    cudaEventRecord(ctx->wave_phase, ctx->wave_streams[0]);
-                    cudaStreamWaitEvent(ctx->wave_streams[1], ctx->wave_phase, 0);
-                    launch(0, 0, 2, 4);
-                    launch(1, 0, 0, 2);
+                if (groups == 1 || wave > 0) {
+                    for (int g = 0; g < groups; g++) launch(g, wave, 0, 4);
                 } else {
-                    launch(0, wave, 0, 4);
-                    launch(1, wave - 1, 2, 4);
-                    launch(1, wave, 0, 2);
+                    // Stagger the groups: group g starts its first wave when group g - 1 is 4 / groups
+                    // kernels into its own, so memory-bound and issue-bound kernels of different
+                    // groups run side by side from then on.
+                    const int lead = 4 / groups > 0 ? 4 / groups : 1;
+                    for (int g = 0; g < groups; g++) {
+                        if (g > 0) cudaStreamWaitEvent(ctx->wave_streams[g], ctx->wave_phase[g - 1], 0);
+                        launch(g, 0, 0, lead);
+                        cudaEventRecord(ctx->wave_phase[g], ctx->wave_streams[g]);
+                        launch(g, 0, lead, 4);
+                    }
                 }
             }
             cudaError_t ce = cudaGetLastError();
             for (int g = 0; g < groups && ce == cudaSuccess; g++) {
-                cudaStream_t s = groups == 2 ? ctx->wave_streams[g] : ctx->stream;
-                ce = cudaMemcpyAsync(&ctx->wave_live_host[(k & 1u) * 2 + g], &p[g].b.ctrl->live, sizeof(uint32_t),
+                cudaStream_t s = groups >= 2 ? ctx->wave_streams[g] : ctx->stream;
+                ce = cudaMemcpyAsync(&ctx->wave_live_host[(k & 1u) * RtContext::kMaxGroups + g], &p[g].b.ctrl->live, sizeof(uint32_t),
                                      cudaMemcpyDeviceToHost, s);
                 if (ce == cudaSuccess) ce = cudaEventRecord(ctx->wave_events[k & 1u][g], s);
             }
@@ -703,7 +703,7 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
                 uint32_t live = 0;
                 for (int g = 0; g < groups && ce == cudaSuccess; g++) {
                     ce = cudaEventSynchronize(ctx->wave_events[(k - 1u) & 1u][g]);
-                    live += ctx->wave_live_host[((k - 1u) & 1u) * 2 + g];
+                    live += ctx->wave_live_host[((k - 1u) & 1u) * RtContext::kMaxGroups + g];
                 }
                 if (ce == cudaSuccess && live == 0u) break;  // the last chunk ran empty
             }
@@ -716,9 +716,9 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
                 break;
             }
         }
-        if (groups == 2) {
-            // join: the context's stream waits for both groups (group 1's last half wave is empty)
-            for (int g = 0; g < 2; g++) {
+        if (groups >= 2) {
+            // join: the context's stream waits for every group
+            for (int g = 0; g < groups; g++) {
                 cudaEventRecord(ctx->wave_join[g], ctx->wave_streams[g]);
                 cudaStreamWaitEvent(ctx->stream, ctx->wave_join[g], 0);
             }
@@ -773,7 +773,7 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
                         t[1] * 1e3, t[2] * 1e3, t[3] * 1e3);
             }
         }
-        for (int g = 0; g < 2; g++)
+        for (int g = 0; g < groups; g++)
             for (cudaEvent_t ev : tl[g]) cudaEventDestroy(ev);
         cudaEventDestroy(t_begin);
         cudaEventDestroy(t_end);
@@ -873,26 +873,29 @@ int rt_create(int device, RtContext** out) {
         long v = atol(k);
         if (v >= 1 && v <= (1l << 18)) ctx->wave_staging_budget = (size_t)v << 20;
     }
-    if (const char* k = getenv("RT_WAVE_GROUPS")) ctx->wave_groups = atoi(k) >= 2 ? 2 : 1;
+    if (const char* k = getenv("RT_WAVE_GROUPS")) {
+        int v = atoi(k);
+        ctx->wave_groups = v < 1 ? 1 : (v > RtContext::kMaxGroups ? RtContext::kMaxGroups : v);
+    }
     if (const char* k = getenv("RT_WAVE_BLOCKS2")) {  // e.g. "4,4,2,2"
         int v[4];
         if (sscanf(k, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4)
             for (int i = 0; i < 4; i++)
                 if (v[i] >= 1 && v[i] <= 16) ctx->wave_blocks2[i] = v[i];
     }
-    if ((e = cudaHostAlloc(&ctx->wave_live_host, 4 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess)
+    if ((e = cudaHostAlloc(&ctx->wave_live_host, 2 * RtContext::kMaxGroups * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess)
         return bail("cudaHostAlloc", e);
-    for (int g = 0; g < 2; g++) {
+    for (int g = 0; g < RtContext::kMaxGroups; g++) {
         if ((e = cudaStreamCreateWithFlags(&ctx->wave_streams[g], cudaStreamNonBlocking)) != cudaSuccess)
             return bail("cudaStreamCreate", e);
-        if ((e = cudaEventCreateWithFlags(&ctx->wave_join[g], cudaEventDisableTiming)) != cudaSuccess)
+        if ((e = cudaEventCreateWithFlags(&ctx->wave_join[g], cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&ctx->wave_phase[g], cudaEventDisableTiming)) != cudaSuccess)
             return bail("cudaEventCreate", e);
         for (int i = 0; i < 2; i++)
             if ((e = cudaEventCreateWithFlags(&ctx->wave_events[i][g], cudaEventDisableTiming)) != cudaSuccess)
                 return bail("cudaEventCreate", e);
     }
-    if ((e = cudaEventCreateWithFlags(&ctx->wave_fork, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&ctx->wave_phase, cudaEventDisableTiming)) != cudaSuccess)
+    if ((e = cudaEventCreateWithFlags(&ctx->wave_fork, cudaEventDisableTiming)) != cudaSuccess)
         return bail("cudaEventCreate", e);
     *out = ctx;
     return RT_OK;
@@ -909,14 +912,14 @@ void rt_destroy(RtContext* ctx) {
     cudaFree(ctx->wave_arena);
     if (ctx->wave_live_host) cudaFreeHost(ctx->wave_live_host);
     cudaFree(ctx->wave_staging);
-    for (int g = 0; g < 2; g++) {
+    for (int g = 0; g < RtContext::kMaxGroups; g++) {
         for (int i = 0; i < 2; i++)
             if (ctx->wave_events[i][g]) cudaEventDestroy(ctx->wave_events[i][g]);
         if (ctx->wave_join[g]) cudaEventDestroy(ctx->wave_join[g]);
+        if (ctx->wave_phase[g]) cudaEventDestroy(ctx->wave_phase[g]);
         if (ctx->wave_streams[g]) cudaStreamSynchronize(ctx->wave_streams[g]), cudaStreamDestroy(ctx->wave_streams[g]);
     }
     if (ctx->wave_fork) cudaEventDestroy(ctx->wave_fork);
-    if (ctx->wave_phase) cudaEventDestroy(ctx->wave_phase);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
