@@ -178,3 +178,59 @@ def test_degenerate_big_leaf_on_gpu(rt, orc, env_small):
     slots, t = st.first_hit(0)
     oslots, ot, _ = ora.first_hit(0)
     assert np.array_equal(slots, oslots) and t.tobytes() == ot.tobytes()
+
+
+def _random_scene(rt, rng):
+    """Random mix: 0-40 spheres, 0-8 planes (some skewed, some duplicated), cubes and loose
+    triangles, rough and mirror-like materials, a random camera."""
+    b = rt.SceneBuilder()
+    n_mat = int(rng.integers(2, 6))
+    for _ in range(n_mat):
+        b.add_material(rng.uniform(0.1, 1.0, 3), float(rng.choice([0.0, 0.05, 0.3, 1.0])),
+                       float(rng.integers(0, 2)), rng.uniform(0, 0.5, 3) * (rng.random() < 0.25))
+    mat = lambda: int(rng.integers(0, n_mat))
+    for _ in range(int(rng.choice([0, 1, 3, 10, 40]))):
+        b.add_sphere(rng.uniform(-4, 4, 3), float(rng.uniform(0.15, 1.2)), mat())
+    for _ in range(int(rng.choice([0, 1, 2, 8]))):
+        pos = rng.uniform(-5, 5, 3)
+        if rng.random() < 0.5:   # axis-aligned rectangle, like the reference's scenes
+            f, r = (0, 0, float(rng.uniform(2, 10))), (float(rng.uniform(2, 10)), 0, 0)
+        else:                     # skewed parallelogram: sticks out of its two-corner box
+            f, r = rng.uniform(-3, 3, 3), rng.uniform(-3, 3, 3)
+        m = mat()
+        b.add_plane(pos, f, r, m)
+        if rng.random() < 0.3:
+            b.add_plane(pos, f, r, mat())  # the same plane twice (house.toml does this)
+    for _ in range(int(rng.integers(0, 4))):
+        b.add_mesh_obj(_cube_at(rng.uniform(-3, 3, 3), float(rng.uniform(0.3, 1.5))), mat())
+    if rng.random() < 0.7:
+        n = int(rng.integers(3, 60))
+        verts = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+        normals = rng.normal(size=(n, 3)).astype(np.float32)
+        normals /= np.linalg.norm(normals, axis=1, keepdims=True)
+        tris = np.array([[i, i + 1, i + 2, i, i + 1, i + 2] for i in range(n - 2)], dtype=np.uint32)
+        b.add_mesh_raw(verts, normals, tris, mat())
+    elif rng.random() < 0.5:
+        b.add_sphere((0, 0, 0), 0.5, mat())  # make sure the scene is not empty
+    else:
+        b.add_mesh_obj(_cube_at((0, 0, 0)), mat())
+    cam = (float(rng.uniform(-2, 2)), float(rng.uniform(-1, 3)), float(rng.uniform(4, 9)))
+    return b.set_camera(cam, float(rng.uniform(-0.3, 0.3)), float(rng.uniform(-0.3, 0.2)),
+                        float(rng.uniform(0.7, 1.6))).build()
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("RT_FUZZ_SEEDS", "16"))))
+def test_random_scene_fuzz(rt, orc, env_small, seed):
+    rng = np.random.default_rng(1000 + seed)
+    scene = _random_scene(rt, rng)
+    w, h = 96, 64
+    bounces = int(rng.integers(1, 9))
+    st, got = _render(rt, scene, env_small, w, h, 2, bounces, begin=seed)
+    ora = orc.Oracle(scene, env_small, w, h, max_bounces=bounces)
+    want, counters = ora.render(seed, 2)
+    assert got.tobytes() == want.tobytes(), (seed, scene.counts(), _report(got, want))
+    c = st.counters()
+    assert (c["rays"], c["shadow_rays"]) == (counters["rays"], counters["shadow_rays"])
+    slots, t = st.first_hit(seed)
+    oslots, ot, _ = ora.first_hit(seed)
+    assert np.array_equal(slots, oslots) and t.tobytes() == ot.tobytes(), (seed, scene.counts())
