@@ -389,7 +389,7 @@ def main():
             import oracle as orc
             cores = os.cpu_count() or 1
             _, dt1, _ = cpu_oracle_rate(rt, orc, scene, env, width, height, 1)
-            n = max(1, min(32, int(args.cpu_seconds / max(dt1, 1e-3))))
+            n = max(1, min(96, int(args.cpu_seconds / max(dt1, 1e-3))))
             rate, dt, _ = cpu_oracle_rate(rt, orc, scene, env, width, height, n)
             out["cpu_baseline"] = {"value": rate, "unit": "Mrays/s", "cores": cores, "kind": "port",
                                    "sample": f"{n} of {spp} spp of the full {width}x{height} frame "
