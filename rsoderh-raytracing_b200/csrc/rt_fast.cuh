@@ -44,6 +44,7 @@ constexpr int kStackCap = 64;  // the reference's own stack size (shader.wgsl:48
 
 // Pre-pass program limits (hoisting is disabled for scenes beyond them).
 constexpr uint32_t kPreMaxLeaves = 16, kPreMaxBoxes = 64, kPreMaxPrims = 32;
+constexpr uint32_t kTriStride = 3u;  // float4 per primitive slot record
 constexpr uint32_t kPreMaxFloat4 = kPreMaxLeaves + 2 * kPreMaxBoxes + 4 * kPreMaxPrims;
 
 // Device view of a scene in the fast layout.
@@ -335,7 +336,7 @@ RT_DEV bool walk_leaf(const FastScene& sc, const RayCtx& r, bool any_hit, FHit& 
     uint32_t len = (w.cur >> kLeafLenShift) & 31u;
     if (len == kLeafLenEscape) len = sc.big_len[first];
     for (uint32_t slot = first; slot < first + len; slot++) {
-        const float4* p = sc.tri + 3u * (size_t)slot;
+        const float4* p = sc.tri + kTriStride * (size_t)slot;
         const float4 r0 = ld4(p), r1 = ld4(p + 1), r2 = ld4(p + 2);
         if (f_as_i(r0.w) == 2) {
             float t = 0.0f, u = 0.0f, v = 0.0f;
@@ -399,7 +400,7 @@ RT_DEV void reconstruct_fast(const FastScene& sc, V3 o, V3 d, const FHit& h, V3&
         V3 n = normalize(((1.0f - h.u - h.v) * n0 + h.u * n1) + h.v * n2);
         if (dot(n, d) > 0.0f) n = n * -1.0f;
         normal = n;
-        material = f_as_u(ld4(sc.tri + 3u * (size_t)h.rec + 1).w);
+        material = f_as_u(ld4(sc.tri + kTriStride * (size_t)h.rec + 1).w);
         return;
     }
     const float4* p = sc.ana + 4u * (size_t)(h.rec & kRecIndexMask);

@@ -179,7 +179,7 @@ inline void build_fast_layout(const RtSceneDesc& s, FastLayout& out) {
     // ---- triangle and analytic records ----
     out.ana.assign((size_t)(analytic ? analytic : 1) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
     std::vector<uint32_t> slot_of_analytic(analytic, kNone);
-    out.tri.assign((size_t)slots * 3, make_float4(0.f, 0.f, 0.f, 0.f));
+    out.tri.assign((size_t)slots * kTriStride, make_float4(0.f, 0.f, 0.f, 0.f));
     for (uint32_t slot = 0; slot < slots; slot++) {
         const RtPrimitiveInfo& info = s.primitives[slot];
         if (info.primitive_type == 2u) {
@@ -187,13 +187,13 @@ inline void build_fast_layout(const RtSceneDesc& s, FastLayout& out) {
             const RtVec3 &a = s.vertices[t.vertex_0], &b = s.vertices[t.vertex_1], &c = s.vertices[t.vertex_2];
             // edge_0 = b - a, edge_1 = c - a (shader.wgsl:415-416): single f32 subtractions,
             // so hoisting them to upload time leaves every bit unchanged.
-            out.tri[(size_t)slot * 3 + 0] = make_float4(a.x, a.y, a.z, bits(2u));
-            out.tri[(size_t)slot * 3 + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, bits(t.material_id));
-            out.tri[(size_t)slot * 3 + 2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.f);
+            out.tri[(size_t)slot * kTriStride + 0] = make_float4(a.x, a.y, a.z, bits(2u));
+            out.tri[(size_t)slot * kTriStride + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, bits(t.material_id));
+            out.tri[(size_t)slot * kTriStride + 2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.f);
         } else {
             const uint32_t index = info.primitive_type == 0u ? info.index : s.sphere_count + info.index;
             slot_of_analytic[index] = slot;
-            out.tri[(size_t)slot * 3 + 0] = make_float4(bits(index), 0.f, 0.f, bits(info.primitive_type));
+            out.tri[(size_t)slot * kTriStride + 0] = make_float4(bits(index), 0.f, 0.f, bits(info.primitive_type));
         }
     }
     for (uint32_t i = 0; i < s.sphere_count; i++) {

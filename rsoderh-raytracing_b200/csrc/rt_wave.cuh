@@ -135,6 +135,13 @@ RT_DEVONLY void list_push(uint32_t* list, uint32_t* count, bool want, uint32_t e
 #ifndef RT_WAVE_STREAM
 #define RT_WAVE_STREAM 0
 #endif
+// L2 eviction priority of the 256-bit state accesses of shade / finish: 1 = evict first.
+#ifndef RT_L2_HINT_PATH
+#define RT_L2_HINT_PATH 1
+#endif
+#ifndef RT_L2_HINT_RAY
+#define RT_L2_HINT_RAY 0
+#endif
 template <typename T>
 RT_DEVONLY T lds(const T* ptr) {
 #if RT_WAVE_STREAM
@@ -189,8 +196,11 @@ struct PathRegs {
     uint32_t occluded;  // the slot's occlusion byte, fetched with the rest (no dependent load)
 };
 
-RT_DEVONLY void load_path(const WaveParams& p, uint32_t slot, PathRegs& s) {
-    const float4 t4 = lds(&p.b.pTLPI[4u * (size_t)slot + 0u]), l4 = lds(&p.b.pTLPI[4u * (size_t)slot + 1u]), p4 = lds(&p.b.pTLPI[4u * (size_t)slot + 2u]);
+// The 64-byte path record with two 256-bit loads / stores.
+RT_DEVONLY void load_path(const WaveParams& p, uint32_t slot, PathRegs& s, uint4& I) {
+    float4 t4, l4, p4, i4;
+    ld8w<RT_L2_HINT_PATH>(&p.b.pTLPI[4u * (size_t)slot + 0u], t4, l4);
+    ld8w<RT_L2_HINT_PATH>(&p.b.pTLPI[4u * (size_t)slot + 2u], p4, i4);
     s.T = xyz(t4);
     s.last_pdf = t4.w;
     s.L = xyz(l4);
@@ -198,12 +208,14 @@ RT_DEVONLY void load_path(const WaveParams& p, uint32_t slot, PathRegs& s) {
     s.pending = xyz(p4);
     s.flags = f_as_u(p4.w);
     s.occluded = p.b.occl[slot];
+    I = make_uint4(f_as_u(i4.x), f_as_u(i4.y), f_as_u(i4.z), f_as_u(i4.w));
 }
 
-RT_DEVONLY void store_path(const WaveParams& p, uint32_t slot, const PathRegs& s) {
-    sts(&p.b.pTLPI[4u * (size_t)slot + 0u], make_float4(s.T.x, s.T.y, s.T.z, s.last_pdf));
-    sts(&p.b.pTLPI[4u * (size_t)slot + 1u], make_float4(s.L.x, s.L.y, s.L.z, u_as_f(s.rng)));
-    sts(&p.b.pTLPI[4u * (size_t)slot + 2u], make_float4(s.pending.x, s.pending.y, s.pending.z, u_as_f(s.flags)));
+RT_DEVONLY void store_path(const WaveParams& p, uint32_t slot, const PathRegs& s, const uint4 I) {
+    st8<RT_L2_HINT_PATH>(&p.b.pTLPI[4u * (size_t)slot + 0u], make_float4(s.T.x, s.T.y, s.T.z, s.last_pdf),
+        make_float4(s.L.x, s.L.y, s.L.z, u_as_f(s.rng)));
+    st8<RT_L2_HINT_PATH>(&p.b.pTLPI[4u * (size_t)slot + 2u], make_float4(s.pending.x, s.pending.y, s.pending.z, u_as_f(s.flags)),
+        make_float4(u_as_f(I.x), u_as_f(I.y), u_as_f(I.z), u_as_f(I.w)));
 }
 
 // shader.wgsl:1249-1264: the last next-event sample counts iff nothing blocked its ray.
@@ -280,10 +292,12 @@ __global__ void __launch_bounds__(kShadeThreads, RT_WAVE_SHADE_MIN_BLOCKS) wave_
         bool emit_closest = false, emit_shadow = false;
         if (on) {
             PathRegs s;
-            load_path(p, slot, s);
+            uint4 I;
+            load_path(p, slot, s, I);
             settle_shadow(p, slot, s);
-            uint4 I = lds((const uint4*)&p.b.pTLPI[4u * (size_t)slot + 3u]);
-            const float4 o4 = lds(&p.b.rOD[2u * (size_t)slot + 0u]), d4 = lds(&p.b.rOD[2u * (size_t)slot + 1u]), h4 = lds(&p.b.hit[slot]);
+            float4 o4, d4;
+            ld8w<RT_L2_HINT_RAY>(&p.b.rOD[2u * (size_t)slot], o4, d4);
+            const float4 h4 = lds(&p.b.hit[slot]);
             FHit hit;
             hit.t = h4.x;
             hit.rec = f_as_u(h4.y);
@@ -303,19 +317,19 @@ __global__ void __launch_bounds__(kShadeThreads, RT_WAVE_SHADE_MIN_BLOCKS) wave_
                 n_shadow++;
             }
             // Both rays start at the hit point (no offset: shader.wgsl:1249, 1295).
-            sts(&p.b.rOD[2u * (size_t)slot + 0u], make_float4(so.point.x, so.point.y, so.point.z, RT_INFINITY));
+            const float4 point4 = make_float4(so.point.x, so.point.y, so.point.z, RT_INFINITY);
             if (done) {
                 // With a shadow ray in flight the sample is finished one wave later.
                 I.w = emit_shadow ? SLOT_ENDING : SLOT_DONE;
                 p.b.stage[slot] = emit_shadow ? STAGE_FINISH_NEXT : STAGE_FINISH;
+                sts(&p.b.rOD[2u * (size_t)slot + 0u], point4);
             } else {
                 emit_closest = true;
-                sts(&p.b.rOD[2u * (size_t)slot + 1u], make_float4(so.next_dir.x, so.next_dir.y, so.next_dir.z, u_as_f(kNone)));
+                st8<RT_L2_HINT_RAY>(&p.b.rOD[2u * (size_t)slot], point4, make_float4(so.next_dir.x, so.next_dir.y, so.next_dir.z, u_as_f(kNone)));
                 p.b.stage[slot] = STAGE_FLIGHT;
                 n_rays++;
             }
-            sts((uint4*)&p.b.pTLPI[4u * (size_t)slot + 3u], I);
-            store_path(p, slot, s);
+            store_path(p, slot, s, I);
         }
         list_push2(rayq, &c->ray_n[P], emit_closest, slot, emit_shadow, slot | kShadowBit);
     });
@@ -344,8 +358,7 @@ __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wav
         if (on) {
             // Everything the slot may need is requested at once (no load waits on another);
             // a new slot's record is uninitialised and ignored.
-            I = lds((const uint4*)&p.b.pTLPI[4u * (size_t)slot + 3u]);
-            load_path(p, slot, s);
+            load_path(p, slot, s, I);
             d4 = lds(&p.b.rOD[2u * (size_t)slot + 1u]);
         }
         // ---- hand out the next path indices: one atomic per warp, in flight during the sky lookup ----
@@ -384,6 +397,7 @@ __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wav
                 I.w = SLOT_RETIRED;
                 p.b.stage[slot] = STAGE_IDLE;
                 retire = true;
+                sts((uint4*)&p.b.pTLPI[4u * (size_t)slot + 3u], I);
             } else {
                 I.x = py * p.width + px;
                 I.y = p.batch_begin + q / p.pixel_ids;
@@ -396,15 +410,13 @@ __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wav
                 s.flags = 0u;
                 I.z = 0u;
                 I.w = SLOT_TRACED;
-                sts(&p.b.rOD[2u * (size_t)slot + 0u], make_float4(o.x, o.y, o.z, RT_INFINITY));
-                sts(&p.b.rOD[2u * (size_t)slot + 1u], make_float4(d.x, d.y, d.z, u_as_f(kNone)));
+                st8<RT_L2_HINT_RAY>(&p.b.rOD[2u * (size_t)slot], make_float4(o.x, o.y, o.z, RT_INFINITY), make_float4(d.x, d.y, d.z, u_as_f(kNone)));
                 p.b.stage[slot] = STAGE_FLIGHT;
-                store_path(p, slot, s);
+                store_path(p, slot, s, I);
                 emit = true;
                 n_paths++;
                 n_rays++;
             }
-            sts((uint4*)&p.b.pTLPI[4u * (size_t)slot + 3u], I);
         }
         list_push(rayq, &c->ray_n[P], emit, slot);
         const unsigned gone = __ballot_sync(0xFFFFFFFFu, retire);
