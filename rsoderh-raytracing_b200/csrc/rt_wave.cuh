@@ -63,13 +63,16 @@ enum SlotStage : uint8_t {
     STAGE_FINISH_NEXT = 4   // path over, last shadow ray in flight: finish in the next wave
 };
 
-// The ray queue is double-buffered by wave parity P = wave & 1: ray_n[P], ray_head[P] are
-// filled by shade(w) + finish(w) and read by prepass(w) + walk(w); shade(w) clears the other.
+// The ray queue is double-buffered by wave parity P = wave & 1: half P (ray_n[P] entries) is
+// filled by shade(w) + finish(w) and read by prepass(w), which writes the rays that still need
+// the triangle walk, compacted, into the idle half Q (walk_n entries) for walk(w) to pull with
+// ray_head[P]. shade(w) clears the counters of half Q and walk_n.
 struct WaveCtrl {
     uint32_t ray_n[2];
     uint32_t ray_head[2];
     uint32_t live;       // slots not yet retired
-    uint32_t pad[3];
+    uint32_t walk_n;     // rays the pre-pass kernel handed on to the walk kernel (this wave)
+    uint32_t pad[2];
 };
 
 struct WaveBuffers {
@@ -285,6 +288,7 @@ __global__ void __launch_bounds__(kShadeThreads, RT_WAVE_SHADE_MIN_BLOCKS) wave_
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         c->ray_n[Q] = 0u;  // next wave's ray queue
         c->ray_head[Q] = 0u;
+        c->walk_n = 0u;
     }
     uint32_t* rayq = p.b.rayq + (size_t)P * 2u * p.slots;
     uint32_t n_rays = 0, n_shadow = 0;
@@ -456,36 +460,63 @@ __global__ void __launch_bounds__(kPrepassThreads, RT_WAVE_PREPASS_MIN_BLOCKS) w
     const uint32_t P = p.wave & 1u;
     WaveCtrl* c = p.b.ctrl;
     const uint32_t count = c->ray_n[P];
-    uint32_t* rayq = p.b.rayq + (size_t)P * 2u * p.slots;
+    const uint32_t* rayq = p.b.rayq + (size_t)P * 2u * p.slots;
+    uint32_t* walkq = p.b.rayq + (size_t)(P ^ 1u) * 2u * p.slots;  // the idle half
     const uint32_t stride = gridDim.x * kPrepassThreads;
-    for (uint32_t i = blockIdx.x * kPrepassThreads + threadIdx.x; i < count; i += stride) {
-        const uint32_t e = rayq[i];
-        const uint32_t slot = e & ~kShadowBit;
-        const bool shadow = (e & kShadowBit) != 0u;
-        const V3 o = xyz(lds(&p.b.rOD[2u * (size_t)slot + 0u]));
-        const V3 d = xyz(shadow ? lds(&p.b.sray_d[slot]) : lds(&p.b.rOD[2u * (size_t)slot + 1u]));
-        const RayCtx r = ray_setup(o, d);
-        FHit best;
-        Fallback fb;
-        prepass(p.scene, spre, r, best, fb);
-        float t0_root;
-        const bool root_ok = root_test(p.scene, r, t0_root);
-        Walk w;
-        walk_begin(p.scene, root_ok, t0_root, best, w);
-        const bool walk = w.cur != kNone && !(shadow && best.rec != kNone);
-        if (shadow) {
-            if (best.rec != kNone) p.b.occl[slot] = 1;
-        } else if (walk) {
-            p.b.rOD[2u * (size_t)slot + 0u].w = best.t;
-            p.b.rOD[2u * (size_t)slot + 1u].w = u_as_f(best.rec);
-            sts(&p.b.fb[slot], make_float2(fb.t, u_as_f(fb.index)));
-        } else {
-            resolve_fallback(p.scene, r, fb, best);
-            sts(&p.b.hit[slot], make_float4(best.t, u_as_f(best.rec), best.u, best.v));
-            p.b.stage[slot] = best.rec != kNone ? STAGE_SHADE : STAGE_FINISH;
+    const uint32_t lane = threadIdx.x & 31u;
+    // Rays that go on collect in a per-warp buffer and reach the walk queue 96-128 at a time
+    // (one atomic per warp and iteration on a single counter would be the kernel's bottleneck).
+    // The walk kernel thus pulls from a queue without holes: a lane that drew a settled ray
+    // used to sit out a whole round.
+    __shared__ uint32_t keep[kPrepassThreads / 32][128];
+    uint32_t* mine = keep[threadIdx.x >> 5];
+    uint32_t kept = 0u;
+    auto flush = [&]() {
+        uint32_t base = 0u;
+        if (lane == 0u) base = atomicAdd(&c->walk_n, kept);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        for (uint32_t k = lane; k < kept; k += 32u) walkq[base + k] = mine[k];
+        __syncwarp();
+        kept = 0u;
+    };
+    // every lane of a warp runs the same number of iterations (warp-wide votes inside)
+    for (uint32_t i0 = blockIdx.x * kPrepassThreads + (threadIdx.x & ~31u); i0 < count; i0 += stride) {
+        const uint32_t i = i0 + lane;
+        const uint32_t e = i < count ? rayq[i] : kDeadEntry;
+        bool walk = false;
+        if (e != kDeadEntry) {
+            const uint32_t slot = e & ~kShadowBit;
+            const bool shadow = (e & kShadowBit) != 0u;
+            const V3 o = xyz(lds(&p.b.rOD[2u * (size_t)slot + 0u]));
+            const V3 d = xyz(shadow ? lds(&p.b.sray_d[slot]) : lds(&p.b.rOD[2u * (size_t)slot + 1u]));
+            const RayCtx r = ray_setup(o, d);
+            FHit best;
+            Fallback fb;
+            prepass(p.scene, spre, r, best, fb);
+            float t0_root;
+            const bool root_ok = root_test(p.scene, r, t0_root);
+            Walk w;
+            walk_begin(p.scene, root_ok, t0_root, best, w);
+            walk = w.cur != kNone && !(shadow && best.rec != kNone);
+            if (shadow) {
+                if (best.rec != kNone) p.b.occl[slot] = 1;
+            } else if (walk) {
+                p.b.rOD[2u * (size_t)slot + 0u].w = best.t;
+                p.b.rOD[2u * (size_t)slot + 1u].w = u_as_f(best.rec);
+                sts(&p.b.fb[slot], make_float2(fb.t, u_as_f(fb.index)));
+            } else {
+                resolve_fallback(p.scene, r, fb, best);
+                sts(&p.b.hit[slot], make_float4(best.t, u_as_f(best.rec), best.u, best.v));
+                p.b.stage[slot] = best.rec != kNone ? STAGE_SHADE : STAGE_FINISH;
+            }
         }
-        if (!walk) rayq[i] = kDeadEntry;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, walk);
+        if (walk) mine[kept + __popc(m & ((1u << lane) - 1u))] = e;
+        kept += (uint32_t)__popc(m);
+        __syncwarp();
+        if (kept > 96u) flush();
     }
+    if (kept) flush();
 }
 
 #ifndef RT_WAVE_WALK_MIN_BLOCKS
@@ -497,8 +528,8 @@ __global__ void __launch_bounds__(kPrepassThreads, RT_WAVE_PREPASS_MIN_BLOCKS) w
 __global__ void __launch_bounds__(kWalkThreads, RT_WAVE_WALK_MIN_BLOCKS) wave_walk_kernel(const WaveParams p) {
     const uint32_t P = p.wave & 1u;
     WaveCtrl* c = p.b.ctrl;
-    const uint32_t total = c->ray_n[P];
-    const uint32_t* rayq = p.b.rayq + (size_t)P * 2u * p.slots;
+    const uint32_t total = c->walk_n;
+    const uint32_t* rayq = p.b.rayq + (size_t)(P ^ 1u) * 2u * p.slots;  // compacted by the pre-pass kernel
     const uint32_t lane = threadIdx.x & 31u;
     uint2 stack[kStackCap];
 

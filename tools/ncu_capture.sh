@@ -4,12 +4,14 @@
 # 1. a duration-only pass lists the wave_walk launches; the launch picked is the one in the
 #    middle of the longest-running half (the start-up and drain waves are shorter);
 # 2. the same launch index of each of the four kernels is captured with --set full.
+# NCU_CMD / NCU_KERNELS override the profiled command and the kernels captured.
 # Writes gpurun_out/prof_<tag>_<kernel>.ncu-rep and gpurun_out/ncu_<tag>_pick.txt.
 set -u
 cd "$(dirname "$0")/.."
 tag=${1:-cap}; spp=${2:-32}
 mkdir -p gpurun_out
-cmd="python tools/quick_bench.py $spp 1"
+cmd=${NCU_CMD:-"python tools/quick_bench.py $spp 1"}
+kernels=${NCU_KERNELS:-"walk shade finish prepass"}
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:wave_walk --csv \
     --log-file gpurun_out/ncu_${tag}_list.csv $cmd > gpurun_out/ncu_${tag}_list.log 2>&1
 skip=$(python - "$tag" <<'PY'
@@ -29,7 +31,7 @@ print(pick)
 PY
 )
 cat gpurun_out/ncu_${tag}_pick.txt
-for k in walk shade finish prepass; do
+for k in $kernels; do
   ncu --set full --clock-control none --import-source on -k regex:wave_$k --launch-skip $skip -c 1 \
       -o gpurun_out/prof_${tag}_$k -f $cmd > gpurun_out/ncu_${tag}_$k.log 2>&1
   tail -1 gpurun_out/ncu_${tag}_$k.log
