@@ -24,7 +24,8 @@ if scene_name.startswith("synthetic:"):
 else:
     scene = rt.Scene.load_toml(os.path.join(ROOT, "assets", "scenes", f"{scene_name}.toml"))
 build_s = time.perf_counter() - t0
-env = rt.EnvironmentMaps([rt.Environment.synthetic(2048, 1024)])
+ew, eh = (int(v) for v in os.environ.get("QB_ENV", "2048x1024").split("x"))  # diagnostic: environment size
+env = rt.EnvironmentMaps([rt.Environment.synthetic(ew, eh)])
 st = rt.State(scene, env, w, h, max_bounces=8)
 if os.environ.get("QB_FIRST_HIT"):
     # coherent primary rays only (BASELINE.json configs[2]): kernel + device-to-host copies
