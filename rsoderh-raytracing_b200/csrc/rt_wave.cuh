@@ -340,6 +340,10 @@ __global__ void __launch_bounds__(kShadeThreads, RT_WAVE_SHADE_MIN_BLOCKS) wave_
     fast_flush_counts(0u, n_rays, n_shadow, p.counters);
 }
 
+// 1: the finish kernel runs the analytic pre-pass of the camera rays it creates.
+#ifndef RT_FINISH_PREPASS
+#define RT_FINISH_PREPASS 1
+#endif
 #ifndef RT_WAVE_FINISH_MIN_BLOCKS
 #define RT_WAVE_FINISH_MIN_BLOCKS 8
 #endif
@@ -353,6 +357,27 @@ __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wav
     const float sin_half_fov = rt_sin(p.camera.fov_y / 2.0f);
     const size_t pixels = (size_t)p.width * p.height;
     uint32_t n_paths = 0, n_rays = 0;
+#if RT_FINISH_PREPASS
+    // The camera ray's analytic pre-pass happens right here, while the ray is in registers (this
+    // kernel mostly waits on memory, so the arithmetic is nearly free, and the pre-pass kernel
+    // has a quarter fewer rays to fetch). Rays that go on to the triangle walk are appended to
+    // the walk queue directly, 96-128 at a time per warp.
+    __shared__ float4 spre[kPreMaxFloat4];
+    stage_pre(p.scene, spre);
+    __shared__ uint32_t keep[kFinishThreads / 32][128];
+    uint32_t* mine = keep[threadIdx.x >> 5];
+    uint32_t* walkq = p.b.rayq + (size_t)(P ^ 1u) * 2u * p.slots;
+    uint32_t kept = 0u;
+    auto flush = [&]() {
+        const uint32_t lane = threadIdx.x & 31u;
+        uint32_t base = 0u;
+        if (lane == 0u) base = atomicAdd(&c->walk_n, kept);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        for (uint32_t k = lane; k < kept; k += 32u) walkq[base + k] = mine[k];
+        __syncwarp();
+        kept = 0u;
+    };
+#endif
     sweep_stage<kFinishThreads>(p, STAGE_FINISH, STAGE_FINISH_NEXT, STAGE_FINISH, [&](uint32_t slot, bool on) {
         bool emit = false, retire = false;
         uint4 I = make_uint4(0u, 0u, 0u, SLOT_RETIRED);
@@ -414,18 +439,54 @@ __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wav
                 s.flags = 0u;
                 I.z = 0u;
                 I.w = SLOT_TRACED;
+#if RT_FINISH_PREPASS
+                const RayCtx r = ray_setup(o, d);
+                FHit best;
+                Fallback fb;
+                prepass(p.scene, spre, r, best, fb);
+                float t0_root;
+                const bool root_ok = root_test(p.scene, r, t0_root);
+                Walk w;
+                walk_begin(p.scene, root_ok, t0_root, best, w);
+                emit = w.cur != kNone;  // triangles to test: on to the walk kernel
+                st8<RT_L2_HINT_RAY>(&p.b.rOD[2u * (size_t)slot], make_float4(o.x, o.y, o.z, emit ? best.t : RT_INFINITY),
+                                    make_float4(d.x, d.y, d.z, u_as_f(emit ? best.rec : kNone)));
+                if (emit) {
+                    sts(&p.b.fb[slot], make_float2(fb.t, u_as_f(fb.index)));
+                    p.b.stage[slot] = STAGE_FLIGHT;
+                } else {
+                    resolve_fallback(p.scene, r, fb, best);
+                    sts(&p.b.hit[slot], make_float4(best.t, u_as_f(best.rec), best.u, best.v));
+                    p.b.stage[slot] = best.rec != kNone ? STAGE_SHADE : STAGE_FINISH;
+                }
+#else
                 st8<RT_L2_HINT_RAY>(&p.b.rOD[2u * (size_t)slot], make_float4(o.x, o.y, o.z, RT_INFINITY), make_float4(d.x, d.y, d.z, u_as_f(kNone)));
                 p.b.stage[slot] = STAGE_FLIGHT;
-                store_path(p, slot, s, I);
                 emit = true;
+#endif
+                store_path(p, slot, s, I);
                 n_paths++;
                 n_rays++;
             }
         }
+#if RT_FINISH_PREPASS
+        {
+            const uint32_t lane = threadIdx.x & 31u;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, emit);
+            if (emit) mine[kept + __popc(m & ((1u << lane) - 1u))] = slot;
+            kept += (uint32_t)__popc(m);
+            __syncwarp();
+            if (kept > 96u) flush();
+        }
+#else
         list_push(rayq, &c->ray_n[P], emit, slot);
+#endif
         const unsigned gone = __ballot_sync(0xFFFFFFFFu, retire);
         if (gone && (threadIdx.x & 31u) == 0u) atomicSub(&c->live, (uint32_t)__popc(gone));
     });
+#if RT_FINISH_PREPASS
+    if (kept) flush();
+#endif
     fast_flush_counts(n_paths, n_rays, 0u, p.counters);
 }
 
