@@ -633,6 +633,9 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
         cudaEventRecord(ev, s);
         tl[g].push_back(ev);
     };
+    // Shallow trees walk with their stack in shared memory (RT_WALK_SHALLOW=0: never).
+    static const bool shallow_allowed = !(getenv("RT_WALK_SHALLOW") && atoi(getenv("RT_WALK_SHALLOW")) == 0);
+    const bool shallow = shallow_allowed && ctx->bvh_depth <= rtw::kShallowDepth;
     // One wave of group g: kernels first .. last-1 of (shade, finish, pre-pass, walk).
     auto launch = [&](int g, uint32_t wave, int first, int last) {
         cudaStream_t s = groups >= 2 ? ctx->wave_streams[g] : ctx->stream;
@@ -642,7 +645,8 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
             if (k == 0) rtw::wave_shade_kernel<<<shade_blocks, rtw::kShadeThreads, 0, s>>>(p[g]);
             else if (k == 1) rtw::wave_finish_kernel<<<finish_blocks, rtw::kFinishThreads, 0, s>>>(p[g]);
             else if (k == 2) rtw::wave_prepass_kernel<<<prepass_blocks, rtw::kPrepassThreads, 0, s>>>(p[g]);
-            else rtw::wave_walk_kernel<<<walk_blocks, rtw::kWalkThreads, 0, s>>>(p[g]);
+            else if (shallow) rtw::wave_walk_kernel<true><<<walk_blocks, rtw::kWalkThreads, 0, s>>>(p[g]);
+            else rtw::wave_walk_kernel<false><<<walk_blocks, rtw::kWalkThreads, 0, s>>>(p[g]);
             mark(g, s);
             ctx->launches++;
         }

@@ -293,10 +293,13 @@ RT_DEV void walk_begin(const FastScene& sc, bool root_ok, float t0_root, const F
     w.sp = 0u;
 }
 
-RT_DEV void walk_pop(Walk& w, const uint2* stack) {
+// `stride`: distance between a lane's consecutive stack entries — 1 for a private array, the
+// block size for a shared-memory stack laid out [entry][thread] (conflict-free for any mix of
+// depths in the warp).
+RT_DEV void walk_pop(Walk& w, const uint2* stack, uint32_t stride = 1u) {
     w.cur = kNone;
     while (w.sp > 0u) {
-        const uint2 e = stack[--w.sp];
+        const uint2 e = stack[(--w.sp) * stride];
         if (!(u_as_f(e.y) > w.limit)) {
             w.cur = e.x;
             break;
@@ -306,7 +309,7 @@ RT_DEV void walk_pop(Walk& w, const uint2* stack) {
 
 // One interior record: both children's boxes, near child next, far child pushed.
 template <bool ASSUME_PLAIN = false>
-RT_DEV void walk_node(const FastScene& sc, const RayCtx& r, Walk& w, uint2* stack) {
+RT_DEV void walk_node(const FastScene& sc, const RayCtx& r, Walk& w, uint2* stack, uint32_t stride = 1u) {
     const float4* q = sc.n2 + 4u * (size_t)w.cur;
     const float4 q0 = ld4(q), q1 = ld4(q + 1), q2 = ld4(q + 2), q3 = ld4(q + 3);
     float t0a, t0b;
@@ -320,18 +323,18 @@ RT_DEV void walk_node(const FastScene& sc, const RayCtx& r, Walk& w, uint2* stac
     const float tn0 = second_first ? t0b : t0a, tf0 = second_first ? t0a : t0b;
     if (tn0 != kMiss) {
         w.cur = rn;
-        if (tf0 != kMiss) stack[w.sp++] = make_uint2(rf, f_as_u(tf0));
+        if (tf0 != kMiss) stack[(w.sp++) * stride] = make_uint2(rf, f_as_u(tf0));
     } else if (tf0 != kMiss) {
         w.cur = rf;
     } else {
-        walk_pop(w, stack);
+        walk_pop(w, stack, stride);
     }
 }
 
 // The primitives of the leaf in w.cur, in slot order (shader.wgsl:493-524); then the next
 // node off the stack. Returns true when an any-hit query is settled.
 RT_DEV bool walk_leaf(const FastScene& sc, const RayCtx& r, bool any_hit, FHit& best, Walk& w,
-                      const uint2* stack) {
+                      const uint2* stack, uint32_t stride = 1u) {
     const uint32_t first = w.cur & kLeafSlotMask;
     uint32_t len = (w.cur >> kLeafLenShift) & 31u;
     if (len == kLeafLenEscape) len = sc.big_len[first];
@@ -348,7 +351,7 @@ RT_DEV bool walk_leaf(const FastScene& sc, const RayCtx& r, bool any_hit, FHit& 
         if (any_hit && best.rec != kNone) return true;
     }
     if (!sc.no_prune) w.limit = fminf(RT_INFINITY, best.t * 1.001f);
-    walk_pop(w, stack);
+    walk_pop(w, stack, stride);
     return false;
 }
 

@@ -586,13 +586,22 @@ __global__ void __launch_bounds__(kPrepassThreads, RT_WAVE_PREPASS_MIN_BLOCKS) w
 
 // The triangle walk of every queued ray. Persistent warps; a lane whose ray is finished
 // takes the next queue entry at the next round boundary.
+// SHALLOW: the tree is at most kShallowDepth deep, so the traversal stack fits in shared memory
+// ([entry][thread]: two data-stage passes per push / pop whatever the lanes' depths, where the
+// thread-private stack costs one pass per distinct depth and word — a third of the kernel's
+// load/store work in house.toml).
+constexpr uint32_t kShallowDepth = 8u;
+template <bool SHALLOW>
 __global__ void __launch_bounds__(kWalkThreads, RT_WAVE_WALK_MIN_BLOCKS) wave_walk_kernel(const WaveParams p) {
     const uint32_t P = p.wave & 1u;
     WaveCtrl* c = p.b.ctrl;
     const uint32_t total = c->walk_n;
     const uint32_t* rayq = p.b.rayq + (size_t)(P ^ 1u) * 2u * p.slots;  // compacted by the pre-pass kernel
     const uint32_t lane = threadIdx.x & 31u;
-    uint2 stack[kStackCap];
+    __shared__ uint2 shallow_stack[SHALLOW ? kShallowDepth * kWalkThreads : 1];
+    uint2 deep_stack[SHALLOW ? 1 : kStackCap];
+    uint2* stack = SHALLOW ? shallow_stack + threadIdx.x : deep_stack;
+    constexpr uint32_t kStride = SHALLOW ? (uint32_t)kWalkThreads : 1u;
 
     bool busy = false, any_hit = false;
     uint32_t slot = 0;
@@ -642,12 +651,12 @@ __global__ void __launch_bounds__(kWalkThreads, RT_WAVE_WALK_MIN_BLOCKS) wave_wa
         // Rays with an infinite 1/d component are rare (axis-aligned directions): when the warp
         // holds none, the box tests skip the NaN-safe form without a branch.
         if (__all_sync(0xFFFFFFFFu, !busy || r.plain)) {
-            while (busy && w.cur < kLeafBit) walk_node<true>(p.scene, r, w, stack);
+            while (busy && w.cur < kLeafBit) walk_node<true>(p.scene, r, w, stack, kStride);
         } else {
-            while (busy && w.cur < kLeafBit) walk_node<false>(p.scene, r, w, stack);
+            while (busy && w.cur < kLeafBit) walk_node<false>(p.scene, r, w, stack, kStride);
         }
         bool settled = false;
-        if (busy && w.cur != kNone) settled = walk_leaf(p.scene, r, any_hit, best, w, stack);
+        if (busy && w.cur != kNone) settled = walk_leaf(p.scene, r, any_hit, best, w, stack, kStride);
 
         // ---- lanes whose ray is finished hand over their result ----
         const bool finished = busy && (settled || w.cur == kNone);
