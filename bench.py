@@ -74,6 +74,20 @@ def traversal_bytes(c):
     return 32 * c["nodes_tested"] + 48 * c["tris_tested"]
 
 
+def kernel_algorithmic_bytes(c, pixels):
+    """algorithmic_bytes split over the kernels that do the work (the terms add up to it)."""
+    shaded = c["shaded_bounces"]
+    return {
+        "wave_walk_kernel": traversal_bytes(c),
+        # sphere / plane tests: the analytic pre-pass (the finish kernel runs it for camera rays)
+        "wave_prepass_kernel": 16 * c["spheres_tested"] + 64 * c["planes_tested"],
+        # per shaded hit: normals, material, alias entries and texels of the next-event sample
+        "wave_shade_kernel": 48 * c["tri_hits"] + 16 * c["hits"] + shaded * (2 * 16 + 4 * 16),
+        # sky lookups of escaped rays, accumulation
+        "wave_finish_kernel": (c["env_lookups"] - shaded) * (4 * 16) + 32 * pixels,
+    }
+
+
 def algorithmic_flops(c):
     """FP32 operations, with S_bounce frozen at 250."""
     return (18 * c["nodes_tested"] + 45 * c["tris_tested"] + 30 * c["spheres_tested"] +
@@ -334,20 +348,30 @@ def main():
         sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
         fp32_peak = SM_COUNT * FP32_LANES * 2 * sm_mhz * 1e6 / 1e12
         achieved_tf = alg_flops / render_s / 1e12
-        # dominant kernel = the one with the largest share of the profiled device time
+        # per-kernel rooflines; `roofline` is the one of the dominant kernel (largest share of the
+        # profiled device time)
         kernels = profile["kernels"]
         kernel_total_ms = sum(k["ms"] for k in kernels.values()) or 1.0
-        walk = kernels["wave_walk_kernel"]
-        walk_launches = max(1, walk["launches"])
-        walk_launch_s = walk["ms"] / walk_launches * 1e-3
-        walk_bytes_per_launch = traversal_bytes(counters) * profile["renders"] / walk_launches
-        achieved_gbs = walk_bytes_per_launch / walk_launch_s / 1e9 if walk_launch_s > 0 else 0.0
-        traffic, traffic_note = None, "no ncu capture committed"
-        tpath = os.path.join(ROOT, "profiles", "walk_traffic.json")
+        traffic_by_kernel, traffic_note = {}, "no ncu capture committed"
+        tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as fh:
                 tj = json.load(fh)
-            traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("note", "")
+            traffic_by_kernel, traffic_note = tj.get("kernels", {}), tj.get("note", "")
+        per_kernel_bytes = kernel_algorithmic_bytes(counters, pixels)
+        kernel_rooflines = {}
+        for name, k in kernels.items():
+            n_launch = max(1, k["launches"])
+            launch_s = k["ms"] / n_launch * 1e-3
+            bytes_per_launch = per_kernel_bytes.get(name, 0) * profile["renders"] / n_launch
+            gbs = bytes_per_launch / launch_s / 1e9 if launch_s > 0 else 0.0
+            kernel_rooflines[name] = {
+                "share_of_device_time": k["ms"] / kernel_total_ms, "launch_ms": launch_s * 1e3,
+                "launches_per_step": n_launch // max(1, profile["renders"]),
+                "algorithmic_bytes_per_launch": int(bytes_per_launch), "achieved": gbs, "frac": gbs / hbm_peak,
+                "traffic": traffic_by_kernel.get(name, {}).get("dram_bytes_per_launch")}
+        dominant = max(kernel_rooflines, key=lambda n: kernel_rooflines[n]["share_of_device_time"])
+        dom = kernel_rooflines[dominant]
 
         out = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": n_gpus,
@@ -365,15 +389,18 @@ def main():
                     "d2h_bytes_per_step": pixels * 16, "ms_per_step": total_e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "wave_walk_kernel",
-                         "kernel_share_of_device_time": walk["ms"] / kernel_total_ms,
-                         "algorithmic_bytes_per_launch": int(walk_bytes_per_launch),
-                         "launch_ms": walk_launch_s * 1e3, "launches_per_step": walk_launches // max(1, profile["renders"]),
+            "roofline": {"bound": "hbm", "achieved": dom["achieved"], "peak": hbm_peak, "unit": "GB/s",
+                         "frac": dom["frac"], "traffic": dom["traffic"],
+                         "peak_source": peak_src, "kernel": dominant,
+                         "kernel_share_of_device_time": dom["share_of_device_time"],
+                         "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                         "launch_ms": dom["launch_ms"], "launches_per_step": dom["launches_per_step"],
                          "traffic_note": traffic_note,
-                         "note": "scene is L1/L2 resident and the walk is issue-bound (see roofline_issue); "
-                                 "DRAM traffic is the ray / hit records of the wavefront, not scene data"},
+                         "note": "the scene is L1/L2 resident, so the algorithmic bytes of the walk are served on "
+                                 "chip (its fraction can exceed 1) and the kernels are bound by instruction issue "
+                                 "and by the memory system's rate for scattered 32/64-byte pieces (roofline_issue, "
+                                 "DESIGN.md section 5); the DRAM traffic is the wavefront's own state"},
+            "roofline_kernels": kernel_rooflines,
             "roofline_step": {"bound": "hbm", "achieved": alg_bytes / render_s / 1e9, "peak": hbm_peak,
                               "unit": "GB/s", "frac": alg_bytes / render_s / 1e9 / hbm_peak,
                               "algorithmic_bytes_per_step": int(alg_bytes), "render_ms": render_s * 1e3},
