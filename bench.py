@@ -212,7 +212,20 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the backend has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner (and any NCCL_DEBUG lines) to stdout while the
+        # communicator is created; stdout carries exactly one JSON line, so it points at stderr
+        # until that is done.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     n_gpus = world
 
     width, height, spp = args.width, args.height, args.spp
