@@ -634,7 +634,7 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
         tl[g].push_back(ev);
     };
     // Shallow trees walk with their stack in shared memory (RT_WALK_SHALLOW=0: never).
-    static const bool shallow_allowed = !(getenv("RT_WALK_SHALLOW") && atoi(getenv("RT_WALK_SHALLOW")) == 0);
+    const bool shallow_allowed = !(getenv("RT_WALK_SHALLOW") && atoi(getenv("RT_WALK_SHALLOW")) == 0);
     const bool shallow = shallow_allowed && ctx->bvh_depth <= rtw::kShallowDepth;
     // One wave of group g: kernels first .. last-1 of (shade, finish, pre-pass, walk).
     auto launch = [&](int g, uint32_t wave, int first, int last) {

@@ -56,6 +56,16 @@ def test_slot_pool_and_batches(rt, orc, house, env_small, monkeypatch, slots, st
     assert (got[..., 3] == 1.0).all()
 
 
+def test_walk_stack_in_shared_or_local_memory(rt, house, env_small, monkeypatch):
+    # house.toml is 6 levels deep: its walk keeps the stack in shared memory unless told not to
+    w, h = 160, 90
+    monkeypatch.setenv("RT_WALK_SHALLOW", "1")
+    _, shallow = _render(rt, house, env_small, w, h, 4, 8)
+    monkeypatch.setenv("RT_WALK_SHALLOW", "0")
+    _, deep = _render(rt, house, env_small, w, h, 4, 8)
+    assert shallow.tobytes() == deep.tobytes()
+
+
 def test_progressive_calls_equal_one_call(rt, house, env_small):
     w, h = 128, 72
     st, one = _render(rt, house, env_small, w, h, 7, 8)
