@@ -9,11 +9,15 @@
 //   wave_shade_kernel    slots whose ray hit -> settle last shadow ray, shade (emission,
 //                        next-event set-up, BSDF sample), emit the bounce ray + shadow ray
 //   wave_finish_kernel   slots whose path is over / ray escaped / are new -> settle, sky light,
-//                        park the finished sample, take the next path (camera ray)
-//   wave_prepass_kernel  ray queue -> the analytic pre-pass (rt_fast.cuh) of every emitted ray;
-//                        rays with no triangle to test are finished here and leave the queue
-//   wave_walk_kernel     ray queue -> the triangle walk alone (a few KB of code): persistent
+//                        park the finished sample, take the next path (camera ray) and run that
+//                        ray's analytic pre-pass on the spot (the kernel mostly waits on memory)
+//   wave_prepass_kernel  ray queue -> the analytic pre-pass (rt_fast.cuh) of the rays the shade
+//                        kernel emitted; rays with no triangle to test are finished here, the
+//                        others go, compacted, into the walk queue
+//   wave_walk_kernel     walk queue -> the triangle walk alone (a few KB of code): persistent
 //                        warps whose lanes pull the next ray the moment their own is finished
+//                        (the queue has no holes: a lane that drew a settled entry would sit out
+//                        a whole round)
 // shade and finish find their slots by sweeping a one-byte stage array in slot order and
 // compacting inside the warp (ballot + a small shared-memory list), so a warp's 32 lanes work
 // on 32 NEARBY slots: full lanes and coalesced state traffic, no global lists.
