@@ -307,7 +307,12 @@ int rt_pfm_write_rgb(const char* path, uint32_t width, uint32_t height, const fl
     if (!path || !data || !width || !height || channels_in < 3) return RT_ERR_INVALID_ARGUMENT;
     std::ofstream f(path, std::ios::binary);
     if (!f) return RT_ERR_IO;
-    f << "PF\n" << width << " " << height << "\n-1.0\n";
+    // (snprintf, not operator<<: formatted stream output needs the C++ locale machinery, which
+    // is not reliably initialised when this library is loaded into a process that already
+    // carries another copy of the C++ runtime, e.g. Python with numpy)
+    char header[64];
+    const int header_len = snprintf(header, sizeof header, "PF\n%u %u\n-1.0\n", width, height);
+    f.write(header, header_len);
     std::vector<float> row((size_t)width * 3);
     for (uint32_t y = height; y-- > 0;) {  // PFM stores the bottom row first
         for (uint32_t x = 0; x < width; x++)

@@ -198,3 +198,20 @@ def test_alias_table_properties_full_size(env_2k):
     assert env.leftover_count == int((~assigned).sum())
     # The sun is tiny but holds a large share of the probability mass.
     assert true_pmf[lum.reshape(-1) > 1000].sum() > 0.3
+
+
+def test_image_writers_from_python(rt, tmp_path):
+    # PFM: header, bottom row first, RGB of an RGBA buffer; PNG: signature and size fields.
+    h, w = 5, 7
+    rgba = np.arange(h * w * 4, dtype=np.float32).reshape(h, w, 4)
+    pfm = tmp_path / "a.pfm"
+    rt.write_pfm(str(pfm), rgba)
+    raw = pfm.read_bytes()
+    header = b"PF\n7 5\n-1.0\n"
+    assert raw.startswith(header) and len(raw) == len(header) + h * w * 12
+    data = np.frombuffer(raw[len(header):], dtype="<f4").reshape(h, w, 3)
+    assert np.array_equal(data, rgba[::-1, :, :3])
+    png = tmp_path / "a.png"
+    rt.write_png(str(png), (np.arange(h * w * 3) % 256).astype(np.uint8).reshape(h, w, 3))
+    raw = png.read_bytes()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n" and struct.unpack(">II", raw[16:24]) == (w, h)

@@ -177,3 +177,31 @@ def test_sky_only_scene_matches_closed_form(rt, orc, env_small):
         weight = f32(1.0) / (f32(1.0) + pdf * pdf)
         want = sky * weight
         assert np.allclose(acc[y, x, :3], want, rtol=1e-6, atol=1e-7), (x, y, acc[y, x], want)
+
+
+def test_oracle_command_line(rt, orc, tmp_path):
+    # oracle/cli.py writes what the parity checks compare; its outputs equal the API's
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    scene = os.path.join(ROOT, "assets", "scenes", "default.toml")
+    out = {k: str(tmp_path / k) for k in ("a.pfm", "hit.u32", "bvh.bin", "alias.bin", "c.json")}
+    subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "cli.py"), "--scene", scene, "--width", "40",
+                    "--height", "24", "--spp", "2", "--bounces", "3", "--pfm", out["a.pfm"], "--first-hit",
+                    out["hit.u32"], "--bvh", out["bvh.bin"], "--alias", out["alias.bin"], "--counters",
+                    out["c.json"]], check=True, cwd=ROOT)
+    sc = rt.Scene.load_toml(scene)
+    env = rt.EnvironmentMaps([rt.Environment.synthetic(2048, 1024)])
+    o = orc.Oracle(sc, env, 40, 24, max_bounces=3)
+    accum, counters = o.render(0, 2)
+    slots, _t, _c = o.first_hit(0)
+    raw = open(out["a.pfm"], "rb").read()
+    data = np.frombuffer(raw[len(b"PF\n40 24\n-1.0\n"):], dtype="<f4").reshape(24, 40, 3)
+    assert np.array_equal(data, accum[::-1, :, :3])
+    assert np.array_equal(np.fromfile(out["hit.u32"], dtype=np.uint32).reshape(24, 40), slots)
+    c = sc.counts()
+    assert os.path.getsize(out["bvh.bin"]) == 48 * c["bvh_nodes"] + 8 * c["primitives"]
+    assert os.path.getsize(out["alias.bin"]) == 16 * 2048 * 1024
+    report = json.load(open(out["c.json"]))
+    assert report["render_counters"]["rays"] == counters["rays"] and report["counts"] == c
