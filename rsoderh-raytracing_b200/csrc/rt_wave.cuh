@@ -43,10 +43,22 @@ using namespace rtf;
 
 constexpr uint32_t kShadowBit = 0x80000000u;  // ray queue entry: the slot's shadow ray
 constexpr uint32_t kDeadEntry = 0xFFFFFFFFu;  // ray queue entry settled by the pre-pass
-constexpr int kShadeThreads = 128;
-constexpr int kFinishThreads = 128;
-constexpr int kPrepassThreads = 256;
-constexpr int kWalkThreads = 256;
+#ifndef RT_SHADE_THREADS
+#define RT_SHADE_THREADS 128
+#endif
+#ifndef RT_FINISH_THREADS
+#define RT_FINISH_THREADS 128
+#endif
+#ifndef RT_PREPASS_THREADS
+#define RT_PREPASS_THREADS 256
+#endif
+#ifndef RT_WALK_THREADS
+#define RT_WALK_THREADS 256
+#endif
+constexpr int kShadeThreads = RT_SHADE_THREADS;
+constexpr int kFinishThreads = RT_FINISH_THREADS;
+constexpr int kPrepassThreads = RT_PREPASS_THREADS;
+constexpr int kWalkThreads = RT_WALK_THREADS;
 
 // state word of a slot (pTLPI[4 * slot + 3].w)
 enum SlotState : uint32_t {
