@@ -184,18 +184,28 @@ RT_DEV void offer(const FastScene& sc, const RayCtx& r, FHit& best, float t, uin
 
 // An analytic primitive met inside a leaf or in the fallback list of a scene that is not
 // hoisted (many spheres / planes). Cold for the scenes the reference ships.
-RT_COLD void test_analytic_cold(const float4* __restrict__ ana, uint32_t index, V3 o, V3 d,
-                                                float& t_best, uint32_t& rec_best, uint32_t rec_tag) {
+// (Takes and returns the current best by value: reference parameters of an out-of-line
+// function would pin the caller's best hit to local memory for the whole walk.)
+struct BestRec {
+    float t;
+    uint32_t rec;
+};
+RT_COLD BestRec test_analytic_cold(const float4* __restrict__ ana, uint32_t index, V3 o, V3 d, float t_best,
+                                   uint32_t rec_best, uint32_t rec_tag) {
     const float4* p = ana + 4u * (size_t)index;
     float4 r0 = ld4(p), r1 = ld4(p + 1);
     float t = 0.0f;
     bool hit;
     if (f_as_i(r0.w) == 0) hit = test_sphere(o, d, r0, r1, t);
     else hit = test_plane(o, d, r0, r1, ld4(p + 2), ld4(p + 3), t);
+    BestRec out;
+    out.t = t_best;
+    out.rec = rec_best;
     if (hit && t < t_best) {
-        t_best = t;
-        rec_best = rec_tag | index;
+        out.t = t;
+        out.rec = rec_tag | index;
     }
+    return out;
 }
 
 RT_DEV RayCtx ray_setup(V3 o, V3 d) {
@@ -346,7 +356,9 @@ RT_DEV bool walk_leaf(const FastScene& sc, const RayCtx& r, bool any_hit, FHit& 
             if (test_triangle(r.o, r.d, r0, r1, r2, t, u, v))
                 offer(sc, r, best, t, slot, slot, u, v, !sc.hoisted || best.rec < kRecAnalytic);
         } else if (!sc.hoisted) {
-            test_analytic_cold(sc.ana, f_as_u(r0.x), r.o, r.d, best.t, best.rec, kRecAnalytic);
+            const BestRec b = test_analytic_cold(sc.ana, f_as_u(r0.x), r.o, r.d, best.t, best.rec, kRecAnalytic);
+            best.t = b.t;
+            best.rec = b.rec;
         }
         if (any_hit && best.rec != kNone) return true;
     }
@@ -365,7 +377,11 @@ RT_DEV void resolve_fallback(const FastScene& sc, const RayCtx& r, const Fallbac
         }
     } else {
         for (uint32_t i = 0; i < sc.analytic_count; i++)
-            test_analytic_cold(sc.ana, i, r.o, r.d, best.t, best.rec, kRecFallback);
+        {
+            const BestRec b = test_analytic_cold(sc.ana, i, r.o, r.d, best.t, best.rec, kRecFallback);
+            best.t = b.t;
+            best.rec = b.rec;
+        }
     }
 }
 
