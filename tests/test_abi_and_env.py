@@ -215,3 +215,26 @@ def test_image_writers_from_python(rt, tmp_path):
     rt.write_png(str(png), (np.arange(h * w * 3) % 256).astype(np.uint8).reshape(h, w, 3))
     raw = png.read_bytes()
     assert raw[:8] == b"\x89PNG\r\n\x1a\n" and struct.unpack(">II", raw[16:24]) == (w, h)
+
+
+def test_wave_kernels_keep_their_state_in_registers(rt):
+    # Build hygiene read off the ptxas log of the in-tree build: an out-of-line helper with
+    # reference parameters once pinned the best hit of the walk / pre-pass / finish kernels to
+    # local memory (a fifth of the walk's load/store requests). Stack frames: none for pre-pass
+    # and finish, spills only for shade and the shallow walk, the 64-entry stack for the deep walk.
+    log = os.path.join(ROOT, "rsoderh-raytracing_b200", "csrc", "ptxas.log")
+    if not os.path.exists(log):
+        pytest.skip("no ptxas log (library not built in this tree)")
+    text = open(log).read()
+    frames = {}
+    for m in re.finditer(r"Function properties for (\S+)\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores", text):
+        frames[m.group(1)] = (int(m.group(2)), int(m.group(3)))
+    def frame(part):
+        hits = [v for k, v in frames.items() if part in k]
+        assert hits, f"{part} not in the ptxas log"
+        return hits[0]
+    assert frame("wave_prepass_kernel")[0] == 0
+    assert frame("wave_finish_kernel")[0] <= 16
+    assert frame("wave_walk_kernelILb1")[0] <= 32          # stack in shared memory: spills only
+    assert frame("wave_walk_kernelILb0")[0] <= 512 + 32    # 64 x 8-byte stack entries + spills
+    assert frame("wave_shade_kernel")[0] <= 64
