@@ -1,10 +1,14 @@
 // rt_backend.cu — kernels and extern "C" surface of librt_backend.so (include/rt_backend.h).
 //
 // Replaces the reference's device/pipeline layer (src/state.rs) and its compute shader
-// (src/shaders/shader.wgsl) with sm_100a CUDA. One thread owns one pixel and walks that
-// pixel's samples in order (accumulator in registers, one 16-byte store per pixel per
-// launch); a lane whose path ends starts its pixel's next sample at once, so warps stay
-// populated although path lengths differ.
+// (src/shaders/shader.wgsl) with sm_100a CUDA. The render path is the persistent CTA-local
+// wavefront kernel of rt_local.cuh (one asynchronous launch per rt_render). This file holds
+// the C ABI, the uploads, and two cross-check kernels that are NOT the product path:
+// `render_kernel` / `first_hit_kernel` below walk the reference-layout arrays in the
+// reference's order, one thread per pixel, and count node / primitive tests exactly like the
+// oracle (rt_set_detailed_counters; RT_KERNEL=pixel) — the source of the algorithmic work
+// figures bench.py reports. RT_KERNEL=wave / fast select the superseded pipelines of
+// rt_wave.cuh / rt_fast.cuh, kept so the tests can check that every kernel agrees bit for bit.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -26,6 +30,7 @@
 #include "rt_fast.cuh"
 #include "rt_fast_host.hpp"
 #include "rt_wave.cuh"
+#include "rt_local.cuh"
 
 using namespace rtd;
 
@@ -369,6 +374,7 @@ struct RtContext {
     float4* d_tri = nullptr;
     float4* d_ana = nullptr;
     float4* d_pre = nullptr;
+    float4* d_flat = nullptr;
     uint32_t* d_big_len = nullptr;
     uint32_t* d_ana_paths = nullptr;
     rtf::FastScene fast{};
@@ -395,8 +401,17 @@ struct RtContext {
 
     unsigned long long* d_counters = nullptr;
     int sm_count = 0;
-    enum Kernel { KERNEL_WAVE, KERNEL_FAST, KERNEL_PIXEL };
-    Kernel kernel = KERNEL_WAVE;
+    enum Kernel { KERNEL_LOCAL, KERNEL_WAVE, KERNEL_FAST, KERNEL_PIXEL };
+    Kernel kernel = KERNEL_LOCAL;
+    // persistent CTA-local wavefront (rt_local.cuh)
+    void* local_arena = nullptr;
+    size_t local_arena_bytes = 0;
+    uint32_t local_slots = 1024;          // path slots per CTA
+    uint32_t local_window = 16;           // samples per window (power of two)
+    uint32_t local_stage_paths = 8192;    // parked samples per CTA (ring of windows)
+    bool local_flat_allowed = true;
+    size_t local_smem_set[2] = {0, 0};    // dynamic shared memory opted in per kernel form
+    unsigned long long* d_local_profile = nullptr;  // 11 x u64 (LocalParams::profile)
     // wavefront pipeline state (rt_wave.cuh)
     static constexpr int kMaxGroups = 4;
     rtw::WaveBuffers wave[kMaxGroups]{};
@@ -458,6 +473,8 @@ void free_scene(RtContext* ctx) {
     cudaFree(ctx->d_tri);
     cudaFree(ctx->d_ana);
     cudaFree(ctx->d_pre);
+    cudaFree(ctx->d_flat);
+    ctx->d_flat = nullptr;
     cudaFree(ctx->d_big_len);
     cudaFree(ctx->d_ana_paths);
     ctx->d_ana_paths = nullptr;
@@ -785,6 +802,134 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
     return status;
 }
 
+// ---- persistent CTA-local wavefront (rt_local.cuh): one asynchronous launch per render ----
+uint32_t floor_pow2(uint32_t v) {
+    uint32_t r = 1u;
+    while (r * 2u <= v) r *= 2u;
+    return r;
+}
+
+int local_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, uint32_t sample_count,
+                 uint32_t max_bounces) {
+    rtl::LocalParams p;
+    memset(&p, 0, sizeof p);
+    p.scene = ctx->fast;
+    p.env.texture = e.texture;
+    p.env.alias = e.d_alias;
+    p.env.texels = e.d_texels;
+    p.env.width = e.width;
+    p.env.height = e.height;
+    p.camera = ctx->camera;
+    p.accum = ctx->d_accum;
+    p.counters = ctx->d_counters;
+    p.width = ctx->width;
+    p.height = ctx->height;
+    p.tiles_x = (ctx->width + 7u) / 8u;
+    p.tiles_total = p.tiles_x * ((ctx->height + 7u) / 8u);
+    p.sample_begin = sample_begin;
+    p.sample_count = sample_count;
+    p.max_bounces = max_bounces;
+
+    const bool flat = ctx->local_flat_allowed && ctx->fast.flat_leaves > 0u;
+    const uint32_t window = floor_pow2(sample_count < ctx->local_window ? sample_count : ctx->local_window);
+    uint32_t shift = 0;
+    while ((1u << shift) < window) shift++;
+    p.window_shift = shift;
+    uint32_t ring = floor_pow2(ctx->local_stage_paths / (64u * window) > 0u ? ctx->local_stage_paths / (64u * window) : 1u);
+    if (ring > rtl::kRing) ring = rtl::kRing;
+    p.ring_entries = ring;
+    // few samples per tile: take several tiles per atomic so that one grab feeds the slots once
+    const uint64_t per_tile = 64ull * sample_count;
+    uint32_t grab = (uint32_t)((ctx->local_slots + per_tile - 1) / per_tile);
+    p.tile_grab = grab < 1u ? 1u : (grab > 64u ? 64u : grab);
+
+    // no more CTAs than tiles, no more slots than a CTA's share of the paths needs
+    const uint32_t grid_full = (uint32_t)ctx->sm_count * (uint32_t)rtl::kMinBlocks;
+    const uint32_t grid = p.tiles_total < grid_full ? p.tiles_total : grid_full;
+    p.slots = ctx->local_slots;
+
+    const size_t T = (size_t)grid_full * p.slots;
+    const size_t stage_f4 = (size_t)grid_full * ((size_t)ring * window * 64u);
+    // rOD 32 + pTLPI 64 + sray_d 16 + hit 16 + fb 8 + occl 1 per slot, staging, tile counter
+    const size_t bytes = T * (32 + 64 + 16 + 16 + 8 + 1) + 256 + stage_f4 * sizeof(float4) + 256;
+    if (!ctx->local_arena || ctx->local_arena_bytes < bytes) {
+        RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->local_arena);
+        ctx->local_arena = nullptr;
+        ctx->local_arena_bytes = 0;
+        RT_CUDA(ctx, cudaMalloc(&ctx->local_arena, bytes));
+        ctx->local_arena_bytes = bytes;
+    }
+    {
+        char* q = (char*)ctx->local_arena;
+        p.pTLPI = (float4*)q;   q += T * 64;
+        p.rOD = (float4*)q;     q += T * 32;
+        p.sray_d = (float4*)q;  q += T * 16;
+        p.hit = (float4*)q;     q += T * 16;
+        p.staging = (float4*)q; q += stage_f4 * sizeof(float4);
+        p.fb = (float2*)q;      q += T * 8;
+        p.next_tile = (uint32_t*)q; q += 256;
+        p.occl = (uint8_t*)q;
+    }
+    const size_t smem = rtl::smem_layout(p.scene, p.slots, flat).bytes;
+    if (ctx->local_smem_set[flat ? 1 : 0] < smem) {
+        cudaError_t ce = flat ? cudaFuncSetAttribute(rtl::local_wave_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : cudaFuncSetAttribute(rtl::local_wave_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce != cudaSuccess)
+            return fail(ctx, RT_ERR_CUDA, "%zu bytes of shared memory per CTA refused: %s", smem, cudaGetErrorString(ce));
+        ctx->local_smem_set[flat ? 1 : 0] = smem;
+    }
+    RT_CUDA(ctx, cudaMemsetAsync(p.next_tile, 0, sizeof(uint32_t), ctx->stream));
+    static const bool timeline_print = getenv("RT_LOCAL_PROFILE") != nullptr;
+    const bool profiling = ctx->profiling || timeline_print;
+    if (profiling) {
+        if (!ctx->d_local_profile) RT_CUDA(ctx, cudaMalloc(&ctx->d_local_profile, 11 * sizeof(unsigned long long)));
+        RT_CUDA(ctx, cudaMemsetAsync(ctx->d_local_profile, 0, 11 * sizeof(unsigned long long), ctx->stream));
+        p.profile = ctx->d_local_profile;
+        RT_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    }
+    if (flat) rtl::local_wave_kernel<true><<<grid, rtl::kThreads, smem, ctx->stream>>>(p);
+    else rtl::local_wave_kernel<false><<<grid, rtl::kThreads, smem, ctx->stream>>>(p);
+    ctx->launches++;
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "render kernel launch failed: %s", cudaGetErrorString(ce));
+    if (profiling) {
+        // Phase shares of the one launch (clock64 per CTA, thread 0, at the barriers) scaled to its
+        // CUDA-event duration. Profiling makes the call synchronous.
+        unsigned long long h[11];
+        float ms = 0.f;
+        RT_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+        RT_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_local_profile, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        RT_CUDA(ctx, cudaEventSynchronize(ctx->ev_stop));
+        RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        RT_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+        double cyc = 0;
+        for (int i = 0; i < 5; i++) cyc += (double)h[i];
+        if (cyc <= 0) cyc = 1;
+        const double ctas = h[10] ? (double)h[10] : 1.0;
+        // kernel order of RtWaveProfile: shade, finish, pre-pass, walk; bookkeeping goes to gap_ms
+        const int order[4] = {0, 2, 3, 4};
+        ctx->profile.renders++;
+        ctx->profile.waves += (uint64_t)((double)h[9] / ctas + 0.5);
+        for (int j = 0; j < 4; j++) {
+            ctx->profile.launches[j] += 1;
+            ctx->profile.kernel_ms[j] += ms * (double)h[order[j]] / cyc;
+        }
+        ctx->profile.gap_ms += ms * (double)h[1] / cyc;
+        ctx->profile.total_ms += ms;
+        if (timeline_print) {
+            const double w = h[9] ? (double)h[9] : 1.0;
+            fprintf(stderr, "[local profile] %s walk, %u CTAs x %u slots, window %u x ring %u: %.3f ms, %.0f waves per CTA, "
+                    "%.1f us per wave | shade %.1f%% book %.1f%% finish %.1f%% prepass %.1f%% walk %.1f%% | items per wave: "
+                    "shade %.0f finish %.0f rays %.0f walk %.0f\n",
+                    flat ? "flat" : "stack", grid, p.slots, window, ring, ms, (double)h[9] / ctas, ms * 1e3 / ((double)h[9] / ctas),
+                    100.0 * h[0] / cyc, 100.0 * h[1] / cyc, 100.0 * h[2] / cyc, 100.0 * h[3] / cyc, 100.0 * h[4] / cyc,
+                    h[5] / w, h[6] / w, h[7] / w, h[8] / w);
+        }
+    }
+    return RT_OK;
+}
+
 template <bool COUNT>
 cudaError_t launch_render(const RenderParams& p, uint32_t depth, cudaStream_t stream) {
     dim3 grid((p.width + kTileW - 1) / kTileW, (p.height + kTileH - 1) / kTileH);
@@ -868,7 +1013,21 @@ int rt_create(int device, RtContext** out) {
         // Development switch: the reference-order kernels are kept for the detailed work counters.
         if (!strcmp(k, "pixel")) ctx->kernel = RtContext::KERNEL_PIXEL;
         else if (!strcmp(k, "fast")) ctx->kernel = RtContext::KERNEL_FAST;
+        else if (!strcmp(k, "wave")) ctx->kernel = RtContext::KERNEL_WAVE;
     }
+    if (const char* k = getenv("RT_LOCAL_SLOTS")) {
+        long v = atol(k);
+        if (v >= 64 && v <= (long)rtl::kMaxSlots) ctx->local_slots = (uint32_t)v;
+    }
+    if (const char* k = getenv("RT_LOCAL_WINDOW")) {
+        long v = atol(k);
+        if (v >= 1 && v <= 256) ctx->local_window = floor_pow2((uint32_t)v);
+    }
+    if (const char* k = getenv("RT_LOCAL_STAGE")) {
+        long v = atol(k);
+        if (v >= 64 && v <= (1l << 22)) ctx->local_stage_paths = (uint32_t)v;
+    }
+    if (const char* k = getenv("RT_LOCAL_FLAT")) ctx->local_flat_allowed = atoi(k) != 0;
     if (const char* k = getenv("RT_WAVE_SLOTS")) {
         long v = atol(k);
         if (v >= 1024 && v <= (1l << 24)) ctx->wave_max_slots = (uint32_t)v;
@@ -914,6 +1073,8 @@ void rt_destroy(RtContext* ctx) {
     cudaFree(ctx->d_accum_own);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->wave_arena);
+    cudaFree(ctx->local_arena);
+    cudaFree(ctx->d_local_profile);
     if (ctx->wave_live_host) cudaFreeHost(ctx->wave_live_host);
     cudaFree(ctx->wave_staging);
     for (int g = 0; g < RtContext::kMaxGroups; g++) {
@@ -1062,6 +1223,8 @@ int rt_upload_scene(RtContext* ctx, const RtSceneDesc* s) {
             RT_CUDA(ctx, cudaMemcpy(ctx->d_tri, fl.tri.data(), fl.tri.size() * sizeof(float4), cudaMemcpyHostToDevice));
         RT_CUDA(ctx, cudaMemcpy(ctx->d_ana, fl.ana.data(), fl.ana.size() * sizeof(float4), cudaMemcpyHostToDevice));
         RT_CUDA(ctx, cudaMemcpy(ctx->d_pre, fl.pre.data(), fl.pre.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        RT_CUDA(ctx, cudaMalloc(&ctx->d_flat, fl.flat.size() * sizeof(float4)));
+        RT_CUDA(ctx, cudaMemcpy(ctx->d_flat, fl.flat.data(), fl.flat.size() * sizeof(float4), cudaMemcpyHostToDevice));
         if (!fl.big_len.empty()) {
             RT_CUDA(ctx, cudaMalloc(&ctx->d_big_len, fl.big_len.size() * sizeof(uint32_t)));
             RT_CUDA(ctx, cudaMemcpy(ctx->d_big_len, fl.big_len.data(), fl.big_len.size() * sizeof(uint32_t),
@@ -1075,6 +1238,7 @@ int rt_upload_scene(RtContext* ctx, const RtSceneDesc* s) {
         ctx->fast.tri = ctx->d_tri;
         ctx->fast.ana = ctx->d_ana;
         ctx->fast.pre = ctx->d_pre;
+        ctx->fast.flat = ctx->d_flat;
         ctx->fast.big_len = ctx->d_big_len;
         ctx->fast.ana_paths = ctx->d_ana_paths;
     }
@@ -1219,6 +1383,8 @@ int rt_render(RtContext* ctx, uint32_t sample_begin, uint32_t sample_count, uint
         zero_bounce_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(
             ctx->d_accum, count, ctx->d_counters, sample_count);
         e2 = cudaGetLastError();
+    } else if (ctx->kernel == RtContext::KERNEL_LOCAL && !ctx->detailed) {
+        return local_render(ctx, e, sample_begin, sample_count, max_bounces);
     } else if (ctx->kernel == RtContext::KERNEL_WAVE && !ctx->detailed) {
         return wave_render(ctx, e, sample_begin, sample_count, max_bounces);
     } else if (ctx->kernel == RtContext::KERNEL_FAST && !ctx->detailed) {
@@ -1295,7 +1461,7 @@ int rt_first_hit(RtContext* ctx, uint32_t sample_index, uint32_t* slot_out, floa
     p.height = ctx->height;
     p.sample = sample_index;
     cudaEventRecord(ctx->ev_start, ctx->stream);
-    if ((ctx->kernel == RtContext::KERNEL_FAST || ctx->kernel == RtContext::KERNEL_WAVE) && !ctx->detailed) {
+    if (ctx->kernel != RtContext::KERNEL_PIXEL && !ctx->detailed) {
         rtf::FastParams fp;
         memset(&fp, 0, sizeof fp);
         fp.scene = ctx->fast;

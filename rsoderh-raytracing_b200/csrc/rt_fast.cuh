@@ -46,6 +46,12 @@ constexpr int kStackCap = 64;  // the reference's own stack size (shader.wgsl:48
 constexpr uint32_t kPreMaxLeaves = 16, kPreMaxBoxes = 64, kPreMaxPrims = 32;
 constexpr uint32_t kTriStride = 3u;  // float4 per primitive slot record
 constexpr uint32_t kPreMaxFloat4 = kPreMaxLeaves + 2 * kPreMaxBoxes + 4 * kPreMaxPrims;
+// Flat walk program (small effective trees): leaf boxes, then per-octant visiting orders.
+constexpr uint32_t kFlatMaxLeaves = 32;
+constexpr uint32_t kFlatMaxSlots = 192;  // leaf slots of a flat scene (its triangle records fit shared memory)
+constexpr uint32_t kFlatOrderAt = 2 * kFlatMaxLeaves;            // float4 index of order[8][32] (bytes)
+constexpr uint32_t kFlatRankAt = kFlatOrderAt + 8 * 32 / 16;      // float4 index of rank[8][32] (bytes)
+constexpr uint32_t kFlatFloat4 = kFlatRankAt + 8 * 32 / 16;
 
 // Device view of a scene in the fast layout.
 //   n2:   4 x float4 per interior node of the EFFECTIVE tree: (c1.min, ref1) (c1.max, ref2)
@@ -67,6 +73,14 @@ constexpr uint32_t kPreMaxFloat4 = kPreMaxLeaves + 2 * kPreMaxBoxes + 4 * kPreMa
 //         prim_count, -), then the distinct boxes on the reference's paths to those leaves,
 //         parents first (2 x float4, min.w = bits parent box index or kNone), then primitives
 //         (copies of `ana` records).
+//   flat: the "flat walk" program of a scene whose effective tree has at most kFlatMaxLeaves
+//         leaves (flat_leaves > 0; needs hoisting): per leaf its reference box, 2 x float4
+//         (min, bits first slot) (max, bits length); then order[neg][i] = the i-th leaf the
+//         reference's walk visits for a ray with sign mask neg (shader.wgsl:536 at every
+//         interior node), and rank = its inverse, one byte each. A leaf is visited by the
+//         reference iff its own box is hit (every box above contains it and the slab test is
+//         monotone in the box), so testing the leaf boxes alone and going through the hit ones
+//         in that order tests the same triangles in the same order — without a stack.
 //   ana_paths: per analytic primitive its root-to-leaf path in the REFERENCE tree, for
 //         precedes(): [analytic_count] offsets, then words m | axis << 28 | side << 30, ended
 //         by kNone (m = first slot of the node's second child, side = which child holds it).
@@ -79,11 +93,14 @@ struct FastScene {
     const uint32_t* __restrict__ big_len;
     const float4* __restrict__ pre;
     const uint32_t* __restrict__ ana_paths;
+    const float4* __restrict__ flat;
     float root_min[3], root_max[3];  // box of the effective tree's root
     uint32_t root_ref;
     uint32_t analytic_count;
     uint32_t pre_leaves, pre_boxes, pre_prims;
     uint32_t hoisted;
+    uint32_t flat_leaves;  // 0: no flat walk program
+    uint32_t flat_slots;   // leaf slots of a flat scene (its `tri` records are staged in shared memory)
     uint32_t no_prune;  // a plane may stick out of its leaf box (scene.rs:203-207 bounds only two of
                         // its corners) and is not hoisted: the walk must not prune, like the reference
 };
@@ -404,6 +421,68 @@ RT_DEV void trace_fast(const FastScene& sc, const float4* __restrict__ spre, V3 
         while (w.cur < kLeafBit) walk_node(sc, r, w, stack);
         if (w.cur == kNone) break;
         if (walk_leaf(sc, r, any_hit, best, w, stack)) return;
+    }
+    if (!any_hit) resolve_fallback(sc, r, fb, best);
+}
+
+// ---- flat walk (FastScene::flat) ----
+RT_DEV const uint8_t* flat_order(const float4* __restrict__ sflat, uint32_t neg) {
+    return (const uint8_t*)(sflat + kFlatOrderAt) + 32u * neg;
+}
+RT_DEV const uint8_t* flat_rank(const float4* __restrict__ sflat, uint32_t neg) {
+    return (const uint8_t*)(sflat + kFlatRankAt) + 32u * neg;
+}
+
+// Bit i is set iff the i-th leaf in the ray's visiting order has its box hit within `limit`.
+// The loop runs over the leaves in storage order (every lane reads the same box) and files
+// each answer under the leaf's rank for this ray's octant.
+RT_DEV uint32_t flat_mask(const FastScene& sc, const float4* __restrict__ sflat, const RayCtx& r, float limit) {
+    const uint8_t* rank = flat_rank(sflat, r.neg);
+    uint32_t mask = 0u;
+    for (uint32_t leaf = 0; leaf < sc.flat_leaves; leaf++) {
+        float t0;
+        const bool ok = box_test(r, sflat[2u * leaf], sflat[2u * leaf + 1u], limit, t0);
+        mask |= (ok ? 1u : 0u) << rank[leaf];
+    }
+    return mask;
+}
+
+RT_DEV uint32_t lowest_bit(uint32_t m) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__ffs((int)m) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(m);
+#endif
+}
+
+// cast_ray / the occlusion query like trace_fast, over the flat walk program. `sflat` is
+// the (shared-memory) copy of FastScene::flat.
+RT_DEV void trace_flat(const FastScene& sc, const float4* __restrict__ spre, const float4* __restrict__ sflat,
+                       V3 o, V3 d, bool any_hit, FHit& best) {
+    const RayCtx r = ray_setup(o, d);
+    Fallback fb;
+    prepass(sc, spre, r, best, fb);
+    if (any_hit && best.rec != kNone) return;
+    float limit = fminf(RT_INFINITY, best.t * 1.001f);
+    uint32_t mask = flat_mask(sc, sflat, r, limit);
+    const uint8_t* order = flat_order(sflat, r.neg);
+    while (mask) {
+        const uint32_t leaf = order[lowest_bit(mask)];
+        mask &= mask - 1u;
+        const float4 bmin = sflat[2u * leaf], bmax = sflat[2u * leaf + 1u];
+        float t0;
+        if (!box_test(r, bmin, bmax, limit, t0)) continue;  // the limit has shrunk since the mask was taken
+        const uint32_t first = f_as_u(bmin.w), len = f_as_u(bmax.w);
+        for (uint32_t slot = first; slot < first + len; slot++) {
+            const float4* p = sc.tri + kTriStride * (size_t)slot;
+            const float4 r0 = ld4(p), r1 = ld4(p + 1), r2 = ld4(p + 2);
+            if (f_as_i(r0.w) != 2) continue;  // a hoisted sphere / plane sharing the leaf
+            float t = 0.0f, u = 0.0f, v = 0.0f;
+            if (test_triangle(r.o, r.d, r0, r1, r2, t, u, v))
+                offer(sc, r, best, t, slot, slot, u, v, best.rec < kRecAnalytic);
+            if (any_hit && best.rec != kNone) return;
+        }
+        limit = fminf(RT_INFINITY, best.t * 1.001f);
     }
     if (!any_hit) resolve_fallback(sc, r, fb, best);
 }

@@ -17,6 +17,11 @@ inline float bits(uint32_t u) {
     memcpy(&f, &u, 4);
     return f;
 }
+inline uint32_t word(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+}
 
 // ---- fast layout (rt_fast.cuh): N2 interior records, 48-byte triangle records, analytic
 //      records and the pre-pass program. Inputs are already validated. ----
@@ -59,7 +64,7 @@ inline bool scene_has_loose_plane(const RtSceneDesc& s) {
 }
 
 struct FastLayout {
-    std::vector<float4> n2, tri, ana, pre;
+    std::vector<float4> n2, tri, ana, pre, flat;
     std::vector<uint32_t> big_len, ana_paths;
     FastScene view{};
 };
@@ -285,6 +290,54 @@ inline void build_fast_layout(const RtSceneDesc& s, FastLayout& out) {
     out.pre.insert(out.pre.end(), prims.begin(), prims.end());
     if (out.pre.empty()) out.pre.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
 
+    // ---- flat walk program: leaf boxes + the visiting order of the leaves per ray octant ----
+    uint32_t flat_leaves = 0;
+    out.flat.assign(kFlatFloat4, make_float4(0.f, 0.f, 0.f, 0.f));
+    {
+        const size_t interior = root.ref == kNone || (root.ref & kLeafBit) ? 0 : n2.size() / 4;
+        const size_t leaves = root.ref == kNone ? 0 : interior + 1;  // a binary tree without empty children
+        if (hoisted && leaves >= 1 && leaves <= kFlatMaxLeaves && slots <= kFlatMaxSlots) {
+            // storage order = the visiting order of a ray with no negative direction component
+            std::vector<uint32_t> refs;
+            auto visit = [&](auto&& self, uint32_t ref, uint32_t neg, std::vector<uint32_t>& seq) -> void {
+                if (ref & kLeafBit) {
+                    seq.push_back(ref);
+                    return;
+                }
+                const float4* q = &n2[4u * (size_t)ref];
+                const uint32_t c1 = word(q[0].w), c2 = word(q[1].w), axis = word(q[3].w);
+                const bool second_first = ((neg >> axis) & 1u) != 0u;  // shader.wgsl:536
+                self(self, second_first ? c2 : c1, neg, seq);
+                self(self, second_first ? c1 : c2, neg, seq);
+            };
+            visit(visit, root.ref, 0u, refs);
+            flat_leaves = (uint32_t)refs.size();
+            // a leaf's reference box: find it through its first slot
+            std::vector<uint32_t> node_of_first(slots, kNone);
+            for (uint32_t i = 0; i < nodes; i++)
+                if (s.bvh_nodes[i].primitives_len != 0)
+                    node_of_first[s.bvh_nodes[i].primitives_or_second_child_index] = i;
+            for (uint32_t l = 0; l < flat_leaves; l++) {
+                const uint32_t first = refs[l] & kLeafSlotMask;
+                const RtBvhNode& n = s.bvh_nodes[node_of_first[first]];
+                out.flat[2u * l] = make_float4(n.min[0], n.min[1], n.min[2], bits(first));
+                out.flat[2u * l + 1u] = make_float4(n.max[0], n.max[1], n.max[2], bits(n.primitives_len));
+            }
+            uint8_t* order = (uint8_t*)&out.flat[kFlatOrderAt];
+            uint8_t* rank = (uint8_t*)&out.flat[kFlatRankAt];
+            for (uint32_t neg = 0; neg < 8u; neg++) {
+                std::vector<uint32_t> seq;
+                visit(visit, root.ref, neg, seq);
+                for (uint32_t i = 0; i < flat_leaves; i++) {
+                    uint32_t l = 0;
+                    while (refs[l] != seq[i]) l++;
+                    order[32u * neg + i] = (uint8_t)l;
+                    rank[32u * neg + l] = (uint8_t)i;
+                }
+            }
+        }
+    }
+
     FastScene& v = out.view;
     for (int k = 0; k < 3; k++) {
         v.root_min[k] = root.ref == kNone ? 0.f : root.mn[k];
@@ -296,6 +349,8 @@ inline void build_fast_layout(const RtSceneDesc& s, FastLayout& out) {
     v.pre_boxes = pre_boxes;
     v.pre_prims = pre_prims;
     v.hoisted = hoisted ? 1u : 0u;
+    v.flat_leaves = flat_leaves;
+    v.flat_slots = flat_leaves ? slots : 0u;
     v.no_prune = (!hoisted && scene_has_loose_plane(s)) ? 1u : 0u;
 }
 

@@ -38,6 +38,7 @@ void* emu_scene_create(const RtSceneDesc* s) {
     v.ana = e->layout.ana.data();
     v.pre = e->layout.pre.data();
     v.ana_paths = e->layout.ana_paths.data();
+    v.flat = e->layout.flat.data();
     v.big_len = e->layout.big_len.empty() ? nullptr : e->layout.big_len.data();
     v.tri_normals = nullptr;
     v.materials = nullptr;
@@ -48,6 +49,9 @@ void* emu_scene_create(const RtSceneDesc* s) {
 void emu_scene_free(void* h) { delete (EmuScene*)h; }
 
 int emu_scene_hoisted(void* h) { return (int)((EmuScene*)h)->layout.view.hoisted; }
+
+// Leaves of the flat walk program (0: the scene has none and emu_trace_flat must not be used).
+int emu_scene_flat_leaves(void* h) { return (int)((EmuScene*)h)->layout.view.flat_leaves; }
 
 // Structural check of the effective tree: walks every N2 record from the root and verifies
 // that each interior box encloses its children's boxes, that leaf refs are well formed and
@@ -141,6 +145,25 @@ void emu_trace(void* h, uint32_t n, const float* origins, const float* dirs, int
         rtd::V3 o = rtd::v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
         rtd::V3 d = rtd::v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
         rtf::trace_fast(sc, sc.pre, o, d, any_hit != 0, hit, stack);
+        code_out[i] = encode(sc, e->sphere_count, hit.rec);
+        t_out[i] = hit.rec != rtf::kNone ? hit.t : 0.0f;
+        if (uv_out) {
+            uv_out[2 * i] = hit.u;
+            uv_out[2 * i + 1] = hit.v;
+        }
+    }
+}
+
+// The same rays through the flat walk (trace_flat: leaf-box mask + per-octant visiting order).
+void emu_trace_flat(void* h, uint32_t n, const float* origins, const float* dirs, int any_hit,
+                    uint32_t* code_out, float* t_out, float* uv_out) {
+    EmuScene* e = (EmuScene*)h;
+    const rtf::FastScene& sc = e->layout.view;
+    for (uint32_t i = 0; i < n; i++) {
+        rtf::FHit hit;
+        rtd::V3 o = rtd::v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
+        rtd::V3 d = rtd::v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
+        rtf::trace_flat(sc, sc.pre, sc.flat, o, d, any_hit != 0, hit);
         code_out[i] = encode(sc, e->sphere_count, hit.rec);
         t_out[i] = hit.rec != rtf::kNone ? hit.t : 0.0f;
         if (uv_out) {

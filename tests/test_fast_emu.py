@@ -35,6 +35,8 @@ def emu():
     lib.emu_scene_hoisted.argtypes = [C.c_void_p]
     lib.emu_trace.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                               C.c_void_p, C.c_void_p]
+    lib.emu_trace_flat.argtypes = lib.emu_trace.argtypes
+    lib.emu_scene_flat_leaves.argtypes = [C.c_void_p]
     lib.emu_check_layout.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32 * 8)]
     lib.emu_check_layout.restype = C.c_int
     return lib
@@ -59,14 +61,19 @@ class Emu:
     def hoisted(self):
         return bool(self.lib.emu_scene_hoisted(self.h))
 
-    def trace(self, o, d, shadow=False):
+    @property
+    def flat_leaves(self):
+        """Leaves of the flat walk program; 0 when the scene has none (too many leaves, not hoisted)."""
+        return int(self.lib.emu_scene_flat_leaves(self.h))
+
+    def trace(self, o, d, shadow=False, flat=False):
         o = np.ascontiguousarray(o, dtype=np.float32)
         d = np.ascontiguousarray(d, dtype=np.float32)
         n = len(o)
         code = np.empty(n, np.uint32)
         t = np.empty(n, np.float32)
-        self.lib.emu_trace(self.h, n, o.ctypes.data, d.ctypes.data, int(shadow), code.ctypes.data,
-                           t.ctypes.data, None)
+        fn = self.lib.emu_trace_flat if flat else self.lib.emu_trace
+        fn(self.h, n, o.ctypes.data, d.ctypes.data, int(shadow), code.ctypes.data, t.ctypes.data, None)
         return code, t
 
 
@@ -82,15 +89,18 @@ def _random_rays(rng, n, lo, hi):
 
 
 def _check(emu_scene, ora, o, d, what):
-    code, t = emu_scene.trace(o, d)
     ocode, ot = ora.cast_rays(o, d)
-    bad = np.flatnonzero(code != ocode)
-    assert len(bad) == 0, f"{what}: {len(bad)} of {len(o)} hits differ, first {bad[:5]}: " \
-                          f"{code[bad[:5]]} vs {ocode[bad[:5]]} o={o[bad[:2]]} d={d[bad[:2]]}"
-    assert t.tobytes() == ot.tobytes(), f"{what}: distances differ"
-    scode, _ = emu_scene.trace(o, d, shadow=True)
     socc, _ = ora.cast_rays(o, d, shadow=True)
-    assert np.array_equal(scode != 0xFFFFFFFF, socc != 0), f"{what}: shadow-ray occlusion differs"
+    # the stack walk always; the flat walk (leaf-box mask) whenever the scene has its program
+    for flat in ([False, True] if emu_scene.flat_leaves else [False]):
+        tag = f"{what} ({'flat' if flat else 'stack'} walk)"
+        code, t = emu_scene.trace(o, d, flat=flat)
+        bad = np.flatnonzero(code != ocode)
+        assert len(bad) == 0, f"{tag}: {len(bad)} of {len(o)} hits differ, first {bad[:5]}: " \
+                              f"{code[bad[:5]]} vs {ocode[bad[:5]]} o={o[bad[:2]]} d={d[bad[:2]]}"
+        assert t.tobytes() == ot.tobytes(), f"{tag}: distances differ"
+        scode, _ = emu_scene.trace(o, d, shadow=True, flat=flat)
+        assert np.array_equal(scode != 0xFFFFFFFF, socc != 0), f"{tag}: shadow-ray occlusion differs"
     return code, t
 
 
@@ -134,9 +144,23 @@ def test_shipped_scenes_camera_rays(rt, orc, emu, env_small, name, w, h):
     for y in range(h):
         for x in range(w):
             o[y * w + x], d[y * w + x], _ = ora.camera_ray(x, y, 3)
-    code, et = es.trace(o, d)
-    assert np.array_equal(code.reshape(h, w), slots)
-    assert et.tobytes() == t.tobytes()
+    for flat in ([False, True] if es.flat_leaves else [False]):
+        code, et = es.trace(o, d, flat=flat)
+        assert np.array_equal(code.reshape(h, w), slots)
+        assert et.tobytes() == t.tobytes()
+
+
+def test_flat_program_of_shipped_scenes(rt, emu):
+    # house / default fit the flat walk (few triangle leaves); suzanne (hundreds) does not
+    leaves = {}
+    for name in ("house", "default", "suzanne"):
+        scene = rt.Scene.load_toml(os.path.join(ASSETS, "scenes", f"{name}.toml"))
+        es = Emu(emu, scene)
+        _, stats = es.check_layout()
+        leaves[name] = (es.flat_leaves, stats["leaves"])
+    assert leaves["house"][0] == leaves["house"][1] and 0 < leaves["house"][0] <= 32, leaves
+    assert leaves["default"][0] == leaves["default"][1] and 0 < leaves["default"][0] <= 32, leaves
+    assert leaves["suzanne"][0] == 0 and leaves["suzanne"][1] > 32, leaves
 
 
 CUBE = """o cube

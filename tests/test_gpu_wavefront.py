@@ -1,4 +1,6 @@
-"""GPU tests of the wavefront pipeline (rt_wave.cuh) and the fast traversal (rt_fast.cuh):
+"""GPU tests of the render kernels — the persistent CTA-local wavefront (rt_local.cuh, the
+product path), the launch-per-phase wavefront pipeline (rt_wave.cuh) and the fast traversal
+(rt_fast.cuh):
 bit-exact against the oracle and against the backend's other kernels, on the cases the
 shipped scenes do not reach — tiny slot pools and several staging batches, frame sizes
 with partial 8x8 tiles, exact ties across leaves, scenes whose analytic primitives are
@@ -30,14 +32,44 @@ def _report(a, b):
 def test_all_kernels_agree_bit_for_bit(rt, house, env_small, monkeypatch):
     w, h = 200, 112
     images = {}
-    for kernel in ("wave", "fast", "pixel"):
-        monkeypatch.setenv("RT_KERNEL", kernel)
+    for kernel in ("local", "wave", "fast", "pixel"):
+        monkeypatch.setenv("RT_KERNEL", kernel)  # "local" is the default (the product path)
         st, images[kernel] = _render(rt, house, env_small, w, h, 3, 8)
         c = st.counters()
         assert c["paths"] == w * h * 3
         images[kernel + "_counts"] = (c["paths"], c["rays"], c["shadow_rays"])
-    assert images["wave"].tobytes() == images["fast"].tobytes() == images["pixel"].tobytes()
-    assert images["wave_counts"] == images["fast_counts"] == images["pixel_counts"]
+    assert images["local"].tobytes() == images["wave"].tobytes() == images["fast"].tobytes() == images["pixel"].tobytes()
+    assert images["local_counts"] == images["wave_counts"] == images["fast_counts"] == images["pixel_counts"]
+
+
+@pytest.mark.parametrize("slots,stage,window,w,h,spp", [(64, 64, 1, 203, 117, 5), (256, 1024, 4, 320, 180, 9),
+                                                        (1024, 8192, 16, 161, 90, 20), (4096, 65536, 16, 161, 90, 4),
+                                                        (512, 2048, 8, 97, 61, 11)])
+def test_local_pools_windows_and_rings(rt, orc, house, env_small, monkeypatch, slots, stage, window, w, h, spp):
+    # The persistent kernel with tiny pools (every slot traces many paths), a one-window ring
+    # (stage = 64 * window: the slots wait for every commit), windows that do not divide the
+    # sample count, sizes with partial 8x8 tiles: the image must not depend on any of it.
+    monkeypatch.setenv("RT_LOCAL_SLOTS", str(slots))
+    monkeypatch.setenv("RT_LOCAL_STAGE", str(stage))
+    monkeypatch.setenv("RT_LOCAL_WINDOW", str(window))
+    st, got = _render(rt, house, env_small, w, h, spp, 8, begin=3)
+    want, counters = orc.Oracle(house, env_small, w, h, max_bounces=8).render(3, spp)
+    assert got.tobytes() == want.tobytes(), _report(got, want)
+    c = st.counters()
+    assert (c["paths"], c["rays"], c["shadow_rays"]) == (counters["paths"], counters["rays"],
+                                                         counters["shadow_rays"])
+    assert (got[..., 3] == 1.0).all()
+    assert st.launch_count() <= 4  # clear + ONE render launch (+ the uploads' material bake)
+
+
+def test_local_flat_walk_equals_stack_walk(rt, house, env_small, monkeypatch):
+    # house.toml fits the flat walk (18 leaves); RT_LOCAL_FLAT=0 sends it through the N2 stack walk
+    w, h = 160, 90
+    monkeypatch.setenv("RT_LOCAL_FLAT", "1")
+    _, flat = _render(rt, house, env_small, w, h, 4, 8)
+    monkeypatch.setenv("RT_LOCAL_FLAT", "0")
+    _, stack = _render(rt, house, env_small, w, h, 4, 8)
+    assert flat.tobytes() == stack.tobytes()
 
 
 @pytest.mark.parametrize("slots,staging_mb,w,h,spp", [(1024, 1, 203, 117, 5), (4096, 1, 320, 180, 9),
@@ -45,6 +77,7 @@ def test_all_kernels_agree_bit_for_bit(rt, house, env_small, monkeypatch):
 def test_slot_pool_and_batches(rt, orc, house, env_small, monkeypatch, slots, staging_mb, w, h, spp):
     # Few slots: every slot traces many paths; a 1 MB staging budget: several batches
     # (1 MB / (w*h*16 B) samples each); sizes with partial 8x8 tiles: skipped path indices.
+    monkeypatch.setenv("RT_KERNEL", "wave")
     monkeypatch.setenv("RT_WAVE_SLOTS", str(slots))
     monkeypatch.setenv("RT_WAVE_STAGING_MB", str(staging_mb))
     st, got = _render(rt, house, env_small, w, h, spp, 8, begin=3)
@@ -59,6 +92,7 @@ def test_slot_pool_and_batches(rt, orc, house, env_small, monkeypatch, slots, st
 def test_walk_stack_in_shared_or_local_memory(rt, house, env_small, monkeypatch):
     # house.toml is 6 levels deep: its walk keeps the stack in shared memory unless told not to
     w, h = 160, 90
+    monkeypatch.setenv("RT_KERNEL", "wave")
     monkeypatch.setenv("RT_WALK_SHALLOW", "1")
     _, shallow = _render(rt, house, env_small, w, h, 4, 8)
     monkeypatch.setenv("RT_WALK_SHALLOW", "0")
@@ -132,7 +166,8 @@ def test_synthetic_field_deep_tree(rt, orc, env_small):
     assert (slots != 0xFFFFFFFF).mean() > 0.3
 
 
-def test_profile_reports_every_kernel(rt, house, env_small):
+def test_profile_reports_every_kernel(rt, house, env_small, monkeypatch):
+    monkeypatch.setenv("RT_KERNEL", "wave")  # per-kernel event timing of the launch-per-phase pipeline
     st = rt.State(house, env_small, 256, 144, device=0, max_bounces=8)
     st.set_profiling(True)
     st.render_samples(4)
