@@ -1,30 +1,38 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark: Mrays/s on house.toml 1920x1080, 8 bounces.
+"""bench.py — Mrays/s of the per-pixel path-tracing hot path on the BASELINE.json configs.
 
-A "step" is one full render of the frame: `--spp` samples per pixel (default 256, the
-configuration BASELINE.json quotes) of assets/scenes/house.toml at 1920x1080 with
-max_bounces 8 under the synthetic 2048x1024 HDRI, on ONE GPU. With N GPUs every rank
-renders `--spp` samples of the whole frame over a DISJOINT sample-index range
-(rank r: [r*spp, (r+1)*spp)), then the accumulation buffers are sum-reduced onto rank 0
-over NCCL — the sample split of SURVEY §8(e); per-GPU work is fixed, so scaling is "weak".
+`--config` picks the workload (default B, the configuration the metric is quoted on):
+  A  default.toml 640x360, 64 spp, 8 bounces           (the reference's own CPU-runnable case)
+  B  house.toml 1920x1080, 256 spp, 8 bounces          (headline)
+  C  suzanne.toml 3840x2160, primary rays only         (coherent rays; rt_first_hit)
+  D  synthetic 99x99 field, ~10 M triangles, 1920x1080, 16 spp, 8 bounces   (scene > L2)
+  E  house.toml 7680x4320, 1024 spp, 8 bounces         (multi-GPU sample split)
 
-value      = rays traced by all ranks / device time (CUDA events on the launch stream,
-             max over ranks), inputs resident in HBM. Rays are counted in-kernel:
-             closest-hit cast_ray calls + NEE shadow rays (BASELINE.md counting rule).
-e2e        = same metric through the public API with HOST buffers inside the timed
-             region: scene + camera upload (host -> device), render, reduce, and the
-             device -> host read of the W*H*4-float accumulation buffer.
-roofline   = the dominant kernel, wave_walk_kernel (BVH walk): algorithmic bytes of the
-             traversal (32 B per box test + 48 B per triangle test, counted
-             exactly by the reference-order kernel on the same workload, untimed) per
-             launch / the kernel's average launch duration, measured with CUDA events
-             around every launch of the timed region (rt_set_profiling), against the
-             measured HBM copy bandwidth in MEASURED_PEAKS.json. The scene itself is
-             L1/L2 resident; the kernel is issue-bound, which `roofline_issue` (whole
-             step, algorithmic FP32 operations against 148 SM x 128 lanes x 2 x f_SM)
-             and `roofline_step` (all algorithmic bytes of the step) put beside it.
-cpu_baseline / --impl reference = the C++ oracle (a restatement of shader.wgsl; the Rust
-             + wgpu reference cannot be built or run in this image) on all host cores.
+A "step" is one full render of the frame. With N GPUs (one process per GPU under torchrun)
+the frame's samples are SPLIT: rank r renders `split_range(0, spp, r, N)` of the same frame
+(shader.wgsl:1309-1312: a pixel-sample's seed depends only on (pixel, sample index)), then the
+accumulation buffers are sum-reduced onto rank 0 over NCCL: total work is fixed, `"scaling":
+"strong"` (32 spp per GPU at N = 8 for config B). `--scaling weak` keeps the
+round-1 mode (every rank renders `spp` samples of its own range). Before the timed region an
+N > 1 run renders a small frame split N ways, reduces it and compares it on rank 0 with that
+rank's own render of the whole range (`reduce_check`); a mismatch fails the run.
+
+value      = rays traced by all ranks (counted in-kernel by the timed kernels: closest-hit
+             cast_ray calls + NEE shadow rays, BASELINE.md's rule) / device time (CUDA events
+             on the launch stream, max over ranks), inputs resident in HBM.
+e2e        = same metric through the public API with HOST buffers inside the timed region:
+             scene + camera upload, render, reduce, device -> host read of the result.
+roofline   = configs A, B, C, E are bound by instruction issue: algorithmic FP32
+             operations of the step (counted exactly by the reference-order kernel, untimed;
+             18 / 45 / 30 / 40 per node / triangle / sphere / plane test + 250 per shaded
+             bounce) per second, against 148 SMs x 128 lanes x f_SM — the build is
+             --fmad=false, so one operation is one issued instruction. Config D (scene beyond
+             L2) gets the HBM roofline: algorithmic bytes (32 B per box test + 48 B per
+             triangle test + the per-hit / per-bounce terms) per second against the measured
+             copy bandwidth, with the DRAM traffic ncu measured beside it.
+cpu_baseline / --impl reference = the C++ oracle (a restatement of shader.wgsl; the Rust +
+             wgpu reference cannot be built or run in this image) on all host cores, on a
+             bounded sample of the same workload. kind = "port".
 """
 import argparse
 import json
@@ -39,9 +47,21 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-WIDTH, HEIGHT, BOUNCES = 1920, 1080, 8
-SCENE = os.path.join(ROOT, "assets", "scenes", "house.toml")
-WORKLOAD = "house.toml 1920x1080 256spp 8 bounces, synthetic 2048x1024 HDRI (BASELINE.json configs[1])"
+BOUNCES = 8
+CONFIGS = {
+    "A": dict(scene="default", width=640, height=360, spp=64, mode="path",
+              workload="default.toml 640x360 64spp 8 bounces, synthetic 2048x1024 HDRI (BASELINE.json configs[0])"),
+    "B": dict(scene="house", width=1920, height=1080, spp=256, mode="path",
+              workload="house.toml 1920x1080 256spp 8 bounces, synthetic 2048x1024 HDRI (BASELINE.json configs[1])"),
+    "C": dict(scene="suzanne", width=3840, height=2160, spp=1, mode="first_hit",
+              workload="suzanne.toml 3840x2160 primary rays only, first-hit slot map (BASELINE.json configs[2])"),
+    "D": dict(scene="synthetic:99", width=1920, height=1080, spp=16, mode="path",
+              workload="synthetic field 99x99 instances = 9 997 020 triangles, 1920x1080 16spp 8 bounces "
+                       "(BASELINE.json configs[3])"),
+    "E": dict(scene="house", width=7680, height=4320, spp=1024, mode="path",
+              workload="house.toml 7680x4320 1024spp 8 bounces, sample split + NCCL sum-reduce "
+                       "(BASELINE.json configs[4])"),
+}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 SM_COUNT, FP32_LANES = 148, 128
 
@@ -52,44 +72,49 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--spp", type=int, default=256, help="samples per pixel per GPU per step")
-    ap.add_argument("--width", type=int, default=WIDTH)
-    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--config", default="B", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--spp", type=int, default=0, help="override the config's samples per pixel")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0,
                     help="target CPU time of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
+def resolve_config(args):
+    cfg = dict(CONFIGS[args.config])
+    cfg["name"] = args.config
+    changed = False
+    for key in ("spp", "width", "height"):
+        v = getattr(args, key)
+        if v and v != cfg[key]:
+            cfg[key] = v
+            changed = True
+    if changed:
+        cfg["workload"] = (f"{cfg['scene']} {cfg['width']}x{cfg['height']} {cfg['spp']}spp 8 bounces "
+                           f"(config {args.config} at a non-default size)")
+    return cfg
+
+
+def load_scene(rt, cfg):
+    if cfg["scene"].startswith("synthetic:"):
+        return rt.Scene.synthetic_field(os.path.join(ROOT, "assets"), int(cfg["scene"].split(":")[1]))
+    return rt.Scene.load_toml(os.path.join(ROOT, "assets", "scenes", f"{cfg['scene']}.toml"))
+
+
+# ---- algorithmic work ------------------------------------------------------------
 def algorithmic_bytes(c, pixels):
-    """bytes any traversal in the reference's order must touch."""
+    """Bytes any traversal in the reference's order must touch."""
     shaded = c["shaded_bounces"]
     return (32 * c["nodes_tested"] + 48 * c["tris_tested"] + 16 * c["spheres_tested"] +
             64 * c["planes_tested"] + 48 * c["tri_hits"] + 16 * c["hits"] +
             shaded * (2 * 16) + c["env_lookups"] * (4 * 16) + 32 * pixels)
 
 
-def traversal_bytes(c):
-    """The walk kernel's share of algorithmic_bytes: box tests + triangle tests."""
-    return 32 * c["nodes_tested"] + 48 * c["tris_tested"]
-
-
-def kernel_algorithmic_bytes(c, pixels):
-    """algorithmic_bytes split over the kernels that do the work (the terms add up to it)."""
-    shaded = c["shaded_bounces"]
-    return {
-        "wave_walk_kernel": traversal_bytes(c),
-        # sphere / plane tests: the analytic pre-pass (the finish kernel runs it for camera rays)
-        "wave_prepass_kernel": 16 * c["spheres_tested"] + 64 * c["planes_tested"],
-        # per shaded hit: normals, material, alias entries and texels of the next-event sample
-        "wave_shade_kernel": 48 * c["tri_hits"] + 16 * c["hits"] + shaded * (2 * 16 + 4 * 16),
-        # sky lookups of escaped rays, accumulation
-        "wave_finish_kernel": (c["env_lookups"] - shaded) * (4 * 16) + 32 * pixels,
-    }
-
-
-def algorithmic_flops(c):
-    """SURVEY §8(d): FP32 operations, with S_bounce frozen at 250."""
+def algorithmic_ops(c):
+    """FP32 operations, with S_bounce frozen at 250."""
     return (18 * c["nodes_tested"] + 45 * c["tris_tested"] + 30 * c["spheres_tested"] +
             40 * c["planes_tested"] + 250 * c["shaded_bounces"])
 
@@ -146,57 +171,99 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def cpu_oracle_rate(rt, orc, scene, env, width, height, spp, threads=0):
+# ---- the CPU arm ------------------------------------------------------------------------------
+def cpu_oracle_rate(orc, scene, env, cfg, spp, threads=0):
     """Times the oracle on `spp` samples of the workload; returns (Mrays/s, seconds, rays)."""
-    ora = orc.Oracle(scene, env, width, height, max_bounces=BOUNCES)
+    ora = orc.Oracle(scene, env, cfg["width"], cfg["height"], max_bounces=BOUNCES)
     t0 = time.perf_counter()
-    _, c = ora.render(0, spp, threads=threads)
+    if cfg["mode"] == "first_hit":
+        rays = 0
+        for s in range(spp):
+            ora.first_hit(s, threads=threads)
+            rays += cfg["width"] * cfg["height"]
+    else:
+        _, c = ora.render(0, spp, threads=threads)
+        rays = c["rays"] + c["shadow_rays"]
     dt = time.perf_counter() - t0
-    rays = c["rays"] + c["shadow_rays"]
     return rays / dt / 1e6, dt, rays
 
 
-def run_reference(args):
+def cpu_sample_text(cfg, n, dt):
+    if cfg["mode"] == "first_hit":
+        return f"{n} full {cfg['width']}x{cfg['height']} primary-ray frame(s) ({dt:.1f} s of CPU work)"
+    return (f"{n} of {cfg['spp']} spp of the full {cfg['width']}x{cfg['height']} frame "
+            f"(samples 0..{n - 1}, {dt:.1f} s of CPU work)")
+
+
+def scene_buffers_check(scene, cfg):
+    """The CPU arm takes its scene arrays from the product's host library; this pins them to the
+    independent numpy restatement (oracle/scene_oracle.py) byte for byte before anything is timed."""
+    if cfg["scene"].startswith("synthetic:"):
+        return "not checked (10 M triangles are beyond the numpy restatement; tests/ cover small fields)"
+    import numpy as np
+    import scene_oracle
+    path = os.path.join(ROOT, "assets", "scenes", f"{cfg['scene']}.toml")
+    ref = scene_oracle.load_scene_toml(path)
+    nodes, ordered = scene_oracle.build_bvh(ref)
+    ok = scene.primitives_words().tolist() == [list(p) for p in ordered]
+    words = scene.bvh_nodes_words()
+    ok = ok and len(words) == len(nodes)
+    if ok:
+        for w, (mn, mx, idx, length, axis) in zip(words, nodes):
+            f = w.view(np.float32)
+            ok = ok and f[0:3].tobytes() == mn.tobytes() and f[4:7].tobytes() == mx.tobytes()
+            ok = ok and (int(w[8]), int(w[9]), int(w[10])) == (idx, length, axis)
+    ok = ok and scene.vertices().tobytes() == ref.vertices.tobytes()
+    ok = ok and scene.normals().tobytes() == ref.normals.tobytes()
+    ok = ok and scene.triangles_words().tolist() == [list(t) for t in ref.triangles]
+    if not ok:
+        raise SystemExit("scene buffers of librt_host.so differ from oracle/scene_oracle.py")
+    return "BVH nodes, primitive order, vertices, normals, triangles byte-identical to oracle/scene_oracle.py"
+
+
+def run_reference(args, cfg):
     """The reference arm: the oracle (CPU restatement of shader.wgsl) on all host cores."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     import _pkg
     rt = _pkg.load()
     import oracle as orc
-    scene = rt.Scene.load_toml(SCENE)
+    scene = load_scene(rt, cfg)
+    check = scene_buffers_check(scene, cfg)
     env = rt.EnvironmentMaps([rt.Environment.synthetic(2048, 1024)])
     cores = os.cpu_count() or 1
-    # Bounded sample: size one step at ~args.cpu_seconds / steps of CPU work.
-    rate1, dt1, _ = cpu_oracle_rate(rt, orc, scene, env, args.width, args.height, 1)
-    budget = max(2.0, args.cpu_seconds)
-    spp = max(1, min(16, int(budget / max(dt1, 1e-3))))
+    # Bounded sample: size one step at ~args.cpu_seconds of CPU work.
+    _, dt1, _ = cpu_oracle_rate(orc, scene, env, cfg, 1)
+    spp = max(1, min(cfg["spp"], 16, int(max(2.0, args.cpu_seconds) / max(dt1, 1e-3))))
     for _ in range(min(args.warmup, 1)):
-        cpu_oracle_rate(rt, orc, scene, env, args.width, args.height, 1)
+        cpu_oracle_rate(orc, scene, env, cfg, 1)
     total_rays, total_dt = 0, 0.0
     for _ in range(args.steps):
-        _, dt, rays = cpu_oracle_rate(rt, orc, scene, env, args.width, args.height, spp)
+        _, dt, rays = cpu_oracle_rate(orc, scene, env, cfg, spp)
         total_rays += rays
         total_dt += dt
     value = total_rays / total_dt / 1e6
-    sample = f"{spp} of 256 spp of the full 1920x1080 frame per step (samples 0..{spp - 1})"
+    sample = cpu_sample_text(cfg, spp, total_dt / args.steps) + " per step"
     print(json.dumps({
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": total_dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample,
-                   "note": "CPU restatement of shader.wgsl (oracle port); the Rust/wgpu reference cannot be built here"},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                         "sample": sample},
+        "config": {"workload": cfg["workload"], "sample": sample,
+                   "note": "CPU restatement of shader.wgsl (oracle PORT, not the Rust/wgpu reference, which cannot "
+                           "be built here); a rate metric, so the bounded sample stands for the whole frame",
+                   "scene_check": check},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+# ---- the GPU arm ------------------------------------------------------------------------------
 def main():
     args = parse_args()
+    cfg = resolve_config(args)
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, cfg)
         return
 
     import numpy as np
@@ -226,103 +293,22 @@ def main():
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
-    n_gpus = world
 
-    width, height, spp = args.width, args.height, args.spp
+    width, height, spp = cfg["width"], cfg["height"], cfg["spp"]
     pixels = width * height
-    scene = rt.Scene.load_toml(SCENE)
+    first_hit = cfg["mode"] == "first_hit"
+    t_build = time.perf_counter()
+    scene = load_scene(rt, cfg)
+    build_s = time.perf_counter() - t_build
     env = rt.EnvironmentMaps([rt.Environment.synthetic(2048, 1024)])
     state = rt.State(scene, env, width, height, device=local_rank, max_bounces=BOUNCES)
-
-    # The accumulation buffer is a torch tensor so the NCCL reduce can run on it, and the
-    # backend launches on torch's current stream so torch events bracket its kernels.
-    accum = torch.zeros((height, width, 4), dtype=torch.float32, device="cuda")
-    state.bind_accum(accum.data_ptr())
     stream = torch.cuda.current_stream()
-    state.set_stream(stream.cuda_stream)
-    host_accum = torch.empty((height, width, 4), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    sample_begin, _ = rt.samplesplit.weak_range(spp, rank)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    def device_step():
-        accum.zero_()
-        state.render_range(sample_begin, spp)
-        if world > 1:
-            rt.samplesplit.reduce_accumulation(accum, dst=0)
-
-    def e2e_step():
-        # Host buffers -> device (scene arrays, camera), render, reduce, device -> host.
-        state.upload_scene(scene)
-        state.update()
-        accum.zero_()
-        state.render_range(sample_begin, spp)
-        if world > 1:
-            rt.samplesplit.reduce_accumulation(accum, dst=0)
-        host_accum.copy_(accum, non_blocking=True)
-        stream.synchronize()
-
-    # ---- exact work counters of one step (untimed, detailed counting on) ----
-    state.set_detailed_counters(True)
-    state.reset_counters()
-    accum.zero_()
-    state.render_range(sample_begin, spp)
-    counters = state.counters()
-    state.set_detailed_counters(False)
-    rays_per_step = counters["rays"] + counters["shadow_rays"]
-
-    for _ in range(max(args.warmup, 3)):
-        device_step()
-    barrier()
-
-    # ---- timed: device-resident ----
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    launches_before = state.launch_count()
-    step_ms, kernel_ms = [], []
-    for _ in range(args.steps):
-        flush.fill_(1)  # evict L2 between timed iterations
-        barrier()
-        es, e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
-        es.record()
-        accum.zero_()
-        e0.record()
-        state.render_range(sample_begin, spp)
-        e1.record()
-        if world > 1:
-            rt.samplesplit.reduce_accumulation(accum, dst=0)
-        e2.record()
-        barrier()
-        step_ms.append(es.elapsed_time(e2))
-        kernel_ms.append(e0.elapsed_time(e1))
-    launches = state.launch_count() - launches_before
-    # One more step of the same region with CUDA events around every kernel launch
-    # (rt_set_profiling): per-kernel durations for the roofline. Kept out of `value`'s
-    # steps because creating ~10^4 events per step slows the host's launch loop.
-    state.set_profiling(True)
-    flush.fill_(1)
-    barrier()
-    device_step()
-    barrier()
-    profile = state.profile()
-    state.set_profiling(False)
-    clocks = sampler.stop() if sampler else None
-
-    # ---- timed: end to end with host buffers ----
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    e2e_ms = []
-    for _ in range(args.steps):
-        flush.fill_(1)
-        barrier()
-        t0 = time.perf_counter()
-        e2e_step()
-        barrier()
-        e2e_ms.append((time.perf_counter() - t0) * 1e3)
 
     def max_over_ranks(x):
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
@@ -336,17 +322,174 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    total_ms = max_over_ranks(sum(step_ms))
-    total_kernel_ms = max_over_ranks(sum(kernel_ms))
-    total_e2e_ms = max_over_ranks(sum(e2e_ms))
-    all_rays_per_step = sum_over_ranks(rays_per_step)
-    all_paths_per_step = sum_over_ranks(counters["paths"])
+    steps, warmup = args.steps, max(args.warmup, 3)
+    out = {"metric": "Mrays/s", "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+           "higher_is_better": True, "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+
+    if first_hit:
+        # ---- config C: primary rays only. Every rank renders the whole map (replicas). ----
+        host_maps = (rt.pinned_array((height, width), np.uint32), rt.pinned_array((height, width), np.float32))
+        for _ in range(warmup):
+            state.first_hit(0, out=host_maps)
+        barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        launches_before = state.launch_count()
+        kernel_ms, e2e_ms = [], []
+        for _ in range(steps):
+            flush.fill_(1)
+            barrier()
+            t0 = time.perf_counter()
+            state.first_hit(0, out=host_maps)       # kernel + 2 device -> host copies, synchronous
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+            kernel_ms.append(state.first_hit_kernel_ms())
+            barrier()
+        launches = state.launch_count() - launches_before
+        clocks = sampler.stop() if sampler else None
+        state.set_detailed_counters(True)
+        state.reset_counters()
+        state.first_hit(0, out=host_maps)
+        counters = state.counters()
+        state.set_detailed_counters(False)
+        total_ms = max_over_ranks(sum(kernel_ms))
+        total_e2e_ms = max_over_ranks(sum(e2e_ms))
+        rays_per_step = sum_over_ranks(pixels)
+        scaling = "weak"
+        render_s = total_ms / steps * 1e-3
+        extra_config = {"parallelism": f"replicas x{world} (the path is one frame of primary rays)",
+                        "hit_fraction": float((host_maps[0] != 0xFFFFFFFF).mean())}
+        e2e = {"value": rays_per_step * steps / (total_e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s",
+               "h2d_bytes_per_step": 0, "d2h_bytes_per_step": pixels * 8, "ms_per_step": total_e2e_ms / steps,
+               "note": "rt_first_hit into pinned host maps (rt_host_alloc): kernel + slot map + distance map copies"}
+        profile = None
+    else:
+        # ---- path-traced configs ----
+        if world > 1 and args.scaling == "strong":
+            sample_begin, count = rt.samplesplit.split_range(0, spp, rank, world)
+            scaling = "strong"
+        else:
+            sample_begin, count = rt.samplesplit.weak_range(spp, rank)
+            scaling = "weak"
+
+        # The accumulation buffer is a torch tensor so the NCCL reduce can run on it, and the
+        # backend launches on torch's current stream so torch events bracket its kernels.
+        accum = torch.zeros((height, width, 4), dtype=torch.float32, device="cuda")
+        state.bind_accum(accum.data_ptr())
+        state.set_stream(stream.cuda_stream)
+        host_accum = torch.empty((height, width, 4), dtype=torch.float32).pin_memory()
+
+        reduce_check = None
+        if world > 1:
+            reduce_check = run_reduce_check(rt, torch, dist, scene, env, local_rank, rank, world, stream)
+
+        def render_and_reduce():
+            accum.zero_()
+            if count:
+                state.render_range(sample_begin, count)
+            if world > 1:
+                rt.samplesplit.reduce_accumulation(accum, dst=0)
+
+        def e2e_step():
+            # Host buffers -> device (scene arrays, camera), render, reduce, device -> host.
+            state.upload_scene(scene)
+            state.update()
+            render_and_reduce()
+            host_accum.copy_(accum, non_blocking=True)
+            stream.synchronize()
+
+        for _ in range(warmup):
+            render_and_reduce()
+        barrier()
+
+        # ---- timed: device-resident ----
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        state.reset_counters()
+        launches_before = state.launch_count()
+        step_ms, kernel_ms = [], []
+        for _ in range(steps):
+            flush.fill_(1)  # evict L2 between timed iterations
+            barrier()
+            es, e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            es.record()
+            accum.zero_()
+            e0.record()
+            if count:
+                state.render_range(sample_begin, count)
+            e1.record()
+            if world > 1:
+                rt.samplesplit.reduce_accumulation(accum, dst=0)
+            e2.record()
+            barrier()
+            step_ms.append(es.elapsed_time(e2))
+            kernel_ms.append(e0.elapsed_time(e1))
+        launches = state.launch_count() - launches_before
+        timed = state.counters()   # paths / rays / shadow rays of the timed kernels themselves
+        # One more step with per-kernel timing on (rt_set_profiling), kept out of `value`'s steps.
+        state.set_profiling(True)
+        flush.fill_(1)
+        barrier()
+        render_and_reduce()
+        barrier()
+        profile = state.profile()
+        state.set_profiling(False)
+        clocks = sampler.stop() if sampler else None
+
+        # ---- timed: end to end with host buffers ----
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e2e_ms = []
+        for _ in range(steps):
+            flush.fill_(1)
+            barrier()
+            t0 = time.perf_counter()
+            e2e_step()
+            barrier()
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+
+        # ---- exact algorithmic work (untimed): the reference-order kernel with detailed counting.
+        # Bounded: on frames / sample counts beyond the headline's it runs a sample of this rank's range
+        # and the figures are scaled by the ray count of the timed run.
+        budget = 1920 * 1080 * 256
+        detail_count = count if pixels * count <= budget else max(1, budget // pixels)
+        counters, detail_note = dict(timed), "no samples on this rank"
+        if count:
+            state.set_detailed_counters(True)
+            state.reset_counters()
+            accum.zero_()
+            state.render_range(sample_begin, detail_count)
+            counters = state.counters()
+            state.set_detailed_counters(False)
+            per_step = {k: timed[k] // steps for k in ("paths", "rays", "shadow_rays")}
+            if detail_count == count:
+                if any(counters[k] != per_step[k] for k in per_step):
+                    raise SystemExit(f"ray counters of the timed kernels {per_step} differ from the reference-order "
+                                     f"kernel's {({k: counters[k] for k in per_step})}")
+                detail_note = "exact: the reference-order kernel on the same samples; its ray counts equal the timed kernels'"
+            else:
+                scale = (per_step["rays"] + per_step["shadow_rays"]) / max(1, counters["rays"] + counters["shadow_rays"])
+                counters = {k: int(v * scale) for k, v in counters.items()}
+                detail_note = (f"reference-order kernel on {detail_count} of this rank's {count} samples, scaled by "
+                               f"the timed kernels' ray count (x{scale:.3f})")
+        total_ms = max_over_ranks(sum(step_ms))
+        total_kernel_ms = max_over_ranks(sum(kernel_ms))
+        total_e2e_ms = max_over_ranks(sum(e2e_ms))
+        rays_per_step = sum_over_ranks((timed["rays"] + timed["shadow_rays"]) / steps)
+        paths_per_step = sum_over_ranks(timed["paths"] / steps)
+        render_s = total_kernel_ms / steps * 1e-3
+        extra_config = {"parallelism": f"sample split x{world} + NCCL sum-reduce onto rank 0",
+                        "samples_per_gpu": [rt.samplesplit.split_range(0, spp, r, world)[1] if scaling == "strong"
+                                            else spp for r in range(world)],
+                        "msamples_per_s": paths_per_step * steps / (total_ms * 1e-3) / 1e6,
+                        "render_ms_rank_max": total_kernel_ms / steps,
+                        "reduce_ms": (total_ms - total_kernel_ms) / steps,
+                        "algorithmic_work": detail_note}
+        if reduce_check is not None:
+            out["reduce_check"] = reduce_check
+        e2e = {"value": rays_per_step * steps / (total_e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s",
+               "h2d_bytes_per_step": scene_upload_bytes(scene) + 80,
+               "d2h_bytes_per_step": pixels * 16, "ms_per_step": total_e2e_ms / steps}
 
     if rank == 0:
-        value = all_rays_per_step * args.steps / (total_ms * 1e-3) / 1e6
-        e2e_value = all_rays_per_step * args.steps / (total_e2e_ms * 1e-3) / 1e6
-        msamples = all_paths_per_step * args.steps / (total_ms * 1e-3) / 1e6
-
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             with open(peaks_path) as fh:
@@ -355,88 +498,98 @@ def main():
             sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         else:
             hbm_peak, peak_src, sm_max = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)", 1965.0
-        render_s = total_kernel_ms / args.steps * 1e-3  # rank-0 view of one render (all its launches)
-        alg_bytes = algorithmic_bytes(counters, pixels)
-        alg_flops = algorithmic_flops(counters)
         sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
-        fp32_peak = SM_COUNT * FP32_LANES * 2 * sm_mhz * 1e6 / 1e12
-        achieved_tf = alg_flops / render_s / 1e12
-        # per-kernel rooflines; `roofline` is the one of the dominant kernel (largest share of the
-        # profiled device time)
-        kernels = profile["kernels"]
-        kernel_total_ms = sum(k["ms"] for k in kernels.values()) or 1.0
-        traffic_by_kernel, traffic_note = {}, "no ncu capture committed"
-        tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as fh:
-                tj = json.load(fh)
-            traffic_by_kernel, traffic_note = tj.get("kernels", {}), tj.get("note", "")
-        per_kernel_bytes = kernel_algorithmic_bytes(counters, pixels)
-        kernel_rooflines = {}
-        for name, k in kernels.items():
-            n_launch = max(1, k["launches"])
-            launch_s = k["ms"] / n_launch * 1e-3
-            bytes_per_launch = per_kernel_bytes.get(name, 0) * profile["renders"] / n_launch
-            gbs = bytes_per_launch / launch_s / 1e9 if launch_s > 0 else 0.0
-            kernel_rooflines[name] = {
-                "share_of_device_time": k["ms"] / kernel_total_ms, "launch_ms": launch_s * 1e3,
-                "launches_per_step": n_launch // max(1, profile["renders"]),
-                "algorithmic_bytes_per_launch": int(bytes_per_launch), "achieved": gbs, "frac": gbs / hbm_peak,
-                "traffic": traffic_by_kernel.get(name, {}).get("dram_bytes_per_launch")}
-        dominant = max(kernel_rooflines, key=lambda n: kernel_rooflines[n]["share_of_device_time"])
-        dom = kernel_rooflines[dominant]
-
-        out = {
-            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": n_gpus,
-            "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD if (width, height, spp) == (WIDTH, HEIGHT, 256)
-                       else f"house.toml {width}x{height} {spp}spp 8 bounces (non-default size)",
-                       "spp_per_gpu": spp, "parallelism": f"sample-split x{n_gpus} + NCCL sum-reduce",
-                       "l2": "256 MiB flush write between timed steps",
-                       "rays_per_step": int(all_rays_per_step),
-                       "msamples_per_s": msamples},
-            "e2e": {"value": e2e_value, "unit": "Mrays/s",
-                    "h2d_bytes_per_step": scene_upload_bytes(scene) + 80,
-                    "d2h_bytes_per_step": pixels * 16, "ms_per_step": total_e2e_ms / args.steps},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": dom["achieved"], "peak": hbm_peak, "unit": "GB/s",
-                         "frac": dom["frac"], "traffic": dom["traffic"],
-                         "peak_source": peak_src, "kernel": dominant,
-                         "kernel_share_of_device_time": dom["share_of_device_time"],
-                         "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
-                         "launch_ms": dom["launch_ms"], "launches_per_step": dom["launches_per_step"],
-                         "traffic_note": traffic_note,
-                         "note": "the scene is L1/L2 resident, so the algorithmic bytes of the walk are served on "
-                                 "chip (its fraction can exceed 1) and the kernels are bound by instruction issue "
-                                 "and by the memory system's rate for scattered 32/64-byte pieces (roofline_issue, "
-                                 "DESIGN.md section 5); the DRAM traffic is the wavefront's own state"},
-            "roofline_kernels": kernel_rooflines,
-            "roofline_step": {"bound": "hbm", "achieved": alg_bytes / render_s / 1e9, "peak": hbm_peak,
-                              "unit": "GB/s", "frac": alg_bytes / render_s / 1e9 / hbm_peak,
-                              "algorithmic_bytes_per_step": int(alg_bytes), "render_ms": render_s * 1e3},
-            "roofline_issue": {"bound": "fp32-issue", "achieved": achieved_tf, "peak": fp32_peak,
-                               "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
-                               "sm_mhz": sm_mhz, "algorithmic_flops_per_step": int(alg_flops)},
-            "kernel_profile": {"waves_per_step": profile["waves"] // max(1, profile["renders"]),
-                               "gap_ms_per_step": profile["gap_ms"] / max(1, profile["renders"]),
-                               "ms_per_step": {k: v["ms"] / max(1, profile["renders"]) for k, v in kernels.items()}},
+        # rank 0's share of the step, on rank 0's render time
+        ops, abytes = algorithmic_ops(counters), algorithmic_bytes(counters, pixels)
+        issue_peak = SM_COUNT * FP32_LANES * sm_mhz * 1e6 / 1e12   # one op per lane and clock: no FMA in this build
+        issue = {"bound": "issue", "achieved": ops / render_s / 1e12, "peak": issue_peak, "unit": "Tops/s",
+                 "frac": ops / render_s / 1e12 / issue_peak, "traffic": None,
+                 "algorithmic_ops_per_step": int(ops), "render_ms": render_s * 1e3, "sm_mhz": sm_mhz,
+                 "peak_source": "148 SMs x 128 FP32 lanes x median SM clock under load; the build is --fmad=false "
+                                "(arithmetic contract, DESIGN.md section 2), so an operation is one issued "
+                                "instruction and the FMA-doubled 74 TFLOP/s does not apply",
+                 "kernel": "the whole render (one persistent launch, or the four wave kernels it is cut into)"}
+        hbm = {"bound": "hbm", "achieved": abytes / render_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+               "frac": abytes / render_s / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+               "algorithmic_bytes_per_step": int(abytes), "render_ms": render_s * 1e3}
+        measured = load_measured_profile(cfg["name"])
+        if measured:
+            issue["measured"] = measured.get("issue")
+            hbm["traffic"] = measured.get("dram_bytes_per_step")
+            issue["traffic"] = measured.get("dram_bytes_per_step")
+            hbm["traffic_source"] = issue["traffic_source"] = measured.get("source")
+        out.update({
+            "value": rays_per_step * steps / (total_ms * 1e-3) / 1e6,
+            "ms_per_step": total_ms / steps, "scaling": scaling,
+            "config": dict({"workload": cfg["workload"], "config": cfg["name"],
+                            "l2": "256 MiB flush write between timed steps",
+                            "rays_per_step": int(rays_per_step), "scene_build_s": build_s}, **extra_config),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": hbm if cfg["name"] == "D" else issue,
+            "roofline_other": issue if cfg["name"] == "D" else hbm,
             "counters_per_step_rank0": counters,
-        }
+        })
+        if profile and profile["renders"]:
+            out["kernel_profile"] = {
+                "waves_per_step": profile["waves"] // profile["renders"],
+                "launches_per_step": {k: v["launches"] // profile["renders"] for k, v in profile["kernels"].items()},
+                "ms_per_step": {k: v["ms"] / profile["renders"] for k, v in profile["kernels"].items()},
+                "gap_ms_per_step": profile["gap_ms"] / profile["renders"]}
         if not args.no_cpu_baseline:
             import oracle as orc
             cores = os.cpu_count() or 1
-            _, dt1, _ = cpu_oracle_rate(rt, orc, scene, env, width, height, 1)
-            n = max(1, min(96, int(args.cpu_seconds / max(dt1, 1e-3))))
-            rate, dt, _ = cpu_oracle_rate(rt, orc, scene, env, width, height, n)
+            _, dt1, _ = cpu_oracle_rate(orc, scene, env, cfg, 1)
+            n = max(1, min(cfg["spp"], 96, int(args.cpu_seconds / max(dt1, 1e-3))))
+            rate, dt, _ = cpu_oracle_rate(orc, scene, env, cfg, n)
             out["cpu_baseline"] = {"value": rate, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                                   "sample": f"{n} of {spp} spp of the full {width}x{height} frame "
-                                             f"({dt:.1f} s of CPU work)"}
+                                   "sample": cpu_sample_text(cfg, n, dt)}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_reduce_check(rt, torch, dist, scene, env, local_rank, rank, world, stream):
+    """A small frame split `world` ways and sum-reduced over NCCL must equal rank 0's own render of
+    the whole sample range up to float re-association (SURVEY §8d parity gate 4)."""
+    w, h, spp = 480, 270, 8 * world
+    st = rt.State(scene, env, w, h, device=local_rank, max_bounces=BOUNCES)
+    part = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    st.bind_accum(part.data_ptr())
+    st.set_stream(stream.cuda_stream)
+    begin, count = rt.samplesplit.split_range(0, spp, rank, world)
+    st.render_range(begin, count)
+    rt.samplesplit.reduce_accumulation(part, dst=0)
+    stream.synchronize()
+    result = None
+    if rank == 0:
+        whole = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+        st.bind_accum(whole.data_ptr())
+        st.render_range(0, spp)
+        stream.synchronize()
+        diff = (part[..., :3] - whole[..., :3]).abs().max().item()
+        scale = whole[..., :3].abs().max().item()
+        alpha_ok = bool((part[..., 3] == 1.0).all().item())
+        tol = 1e-5 * spp * max(1.0, scale)
+        result = {"frame": f"{w}x{h}", "spp": spp, "ranks": world, "max_abs_diff": diff, "tolerance": tol,
+                  "max_value": scale, "alpha_is_one": alpha_ok, "ok": bool(diff <= tol and alpha_ok)}
+    st.close()
+    flag = torch.tensor([1 if (result is None or result["ok"]) else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    if int(flag.item()) != 1:
+        if rank == 0:
+            print(json.dumps({"error": "reduce_check failed", "reduce_check": result}))
+        raise SystemExit(3)
+    return result
+
+
+def load_measured_profile(config_name):
+    """ncu-measured figures of the committed capture for this config (profiles/measured.json),
+    written by tools/ncu_summary.py from the .ncu-rep of the same command."""
+    path = os.path.join(ROOT, "profiles", "measured.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        return json.load(fh).get(config_name)
 
 
 def scene_upload_bytes(scene):

@@ -15,6 +15,7 @@
 #ifndef RT_BACKEND_H
 #define RT_BACKEND_H
 
+#include <stddef.h>
 #include <stdint.h>
 #include "rt_types.h"
 
@@ -95,6 +96,12 @@ int rt_first_hit(RtContext* ctx, uint32_t sample_index, uint32_t* slot_out, floa
 /* Device time (CUDA events) of the kernel of the last rt_first_hit call, without its copies. */
 float rt_first_hit_kernel_ms(const RtContext* ctx);
 
+/* Page-locked host memory for output buffers (rt_first_hit, rt_read_accum): device -> host
+ * copies into it run at link speed; any other host memory works too, through the driver's
+ * bounce buffer. Free with rt_host_free. */
+int rt_host_alloc(size_t bytes, void** out);
+void rt_host_free(void* p);
+
 int rt_sync(RtContext* ctx);
 /* Device -> host copy of the W*H*4 accumulation floats (alpha = 1 where rendered). */
 int rt_read_accum(RtContext* ctx, float* rgba_out);
@@ -119,6 +126,17 @@ typedef struct RtWaveProfile {
 } RtWaveProfile;
 int rt_set_profiling(RtContext* ctx, int enabled);   /* also clears the accumulated profile */
 int rt_get_profile(RtContext* ctx, RtWaveProfile* out);
+
+/* Device memory a context takes besides the scene and the environments (64 MiB per 2k
+ * environment): the accumulation buffer (16 B per pixel), the path-slot arena of the render
+ * pipeline (162 B per slot; default 8 Mi slots = 1.3 GB) and the sample-staging planes that
+ * keep the per-pixel addition order of shader.wgsl:1367-1371 (16 B per pixel and staged
+ * sample; default at most 8 GiB, and never more than 3/4 of what the device has free when
+ * rt_render runs). rt_set_memory_budget lowers (or raises) the two knobs; 0 keeps a value.
+ * Measured on house.toml 1080p, 256 spp: 8 GiB staging 7.85 Grays/s, 2 GiB 7.66, 1 GiB 7.55;
+ * 4 Mi slots 7.52, 2 Mi 7.19. rt_get_memory_usage reports what is allocated right now. */
+int rt_set_memory_budget(RtContext* ctx, uint64_t staging_bytes, uint32_t path_slots);
+int rt_get_memory_usage(RtContext* ctx, uint64_t* bytes);
 
 int rt_set_detailed_counters(RtContext* ctx, int enabled);
 int rt_reset_counters(RtContext* ctx);

@@ -408,9 +408,16 @@ class State:
         assert rgba.shape == (self.height, self.width, 4)
         self._check(self._lib.rt_write_accum(self._ctx, rgba.ctypes.data))
 
-    def first_hit(self, sample_index: int = 0):
-        slots = np.empty((self.height, self.width), dtype=np.uint32)
-        t = np.empty((self.height, self.width), dtype=np.float32)
+    def first_hit(self, sample_index: int = 0, out=None):
+        """Primary rays only (rt_first_hit). `out` = (slots, t) arrays to fill — e.g. a pair from
+        pinned_array(), which the device copies into at link speed."""
+        if out is None:
+            slots = np.empty((self.height, self.width), dtype=np.uint32)
+            t = np.empty((self.height, self.width), dtype=np.float32)
+        else:
+            slots, t = out
+            assert slots.shape == (self.height, self.width) and slots.dtype == np.uint32
+            assert t.shape == (self.height, self.width) and t.dtype == np.float32
         self._check(self._lib.rt_first_hit(self._ctx, sample_index, slots.ctypes.data, t.ctypes.data))
         return slots, t
 
@@ -425,6 +432,15 @@ class State:
         return out
 
     # -- counters / timing / interop --
+    def set_memory_budget(self, staging_bytes: int = 0, path_slots: int = 0):
+        """rt_set_memory_budget: upper bounds of the staging planes / path-slot arena (0 keeps)."""
+        self._check(self._lib.rt_set_memory_budget(self._ctx, staging_bytes, path_slots))
+
+    def memory_usage(self) -> int:
+        n = C.c_uint64()
+        self._check(self._lib.rt_get_memory_usage(self._ctx, C.byref(n)))
+        return int(n.value)
+
     def set_detailed_counters(self, enabled: bool):
         self._check(self._lib.rt_set_detailed_counters(self._ctx, int(enabled)))
 
@@ -470,6 +486,93 @@ class State:
 
     def launch_count(self) -> int:
         return int(self._lib.rt_launch_count(self._ctx))
+
+
+class StateGroup:
+    """rt_group_*: one host process driving several GPUs — the frame's sample range is split
+    into contiguous per-GPU ranges and the accumulation buffers are sum-reduced onto the root
+    (SURVEY §8e). After reduce() the root holds the sum with alpha = 1 and the other members
+    are zero again, so render() + reduce() rounds can follow each other (progressive render)."""
+
+    def __init__(self, scene: Scene, environments: EnvironmentMaps, width: int, height: int,
+                 devices: Sequence[int], max_bounces: int = REFERENCE_MAX_BOUNCES, environment_index: int = 0):
+        self._lib = _ffi.backend_lib()
+        self._group = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        st = self._lib.rt_group_create(len(devices), arr, C.byref(self._group))
+        if st:
+            raise RtError(st, (self._lib.rt_last_error(None) or b"").decode())
+        self.size = int(self._lib.rt_group_size(self._group))
+        self.max_bounces, self.environment_index = max_bounces, environment_index
+        self.width, self.height = int(width), int(height)
+        self.sample_count = 0
+        self._keep = (scene, environments)
+        u = scene.camera.uniform()
+        for r in range(self.size):
+            ctx = self.context(r)
+            self._check(r, self._lib.rt_upload_scene(ctx, C.byref(scene.desc)))
+            self._check(r, self._lib.rt_upload_environments(ctx, environments.descs(), len(environments.environments)))
+            self._check(r, self._lib.rt_resize(ctx, width, height))
+            self._check(r, self._lib.rt_set_camera(ctx, C.byref(u)))
+
+    def context(self, rank: int):
+        return C.c_void_p(self._lib.rt_group_context(self._group, rank))
+
+    def _check(self, rank, st):
+        if st:
+            raise RtError(st, (self._lib.rt_last_error(self.context(rank)) or b"").decode())
+
+    def render_samples(self, count: int):
+        self._check(0, self._lib.rt_group_render(self._group, self.sample_count, count, self.max_bounces,
+                                                 self.environment_index))
+        self.sample_count += count
+
+    def reduce(self, root: int = 0):
+        self._check(root, self._lib.rt_group_reduce(self._group, root))
+
+    def sync(self):
+        self._check(0, self._lib.rt_group_sync(self._group))
+
+    def read_accum(self, rank: int = 0) -> np.ndarray:
+        out = np.empty((self.height, self.width, 4), dtype=np.float32)
+        self._check(rank, self._lib.rt_read_accum(self.context(rank), out.ctypes.data))
+        return out
+
+    def counters(self, rank: int) -> dict:
+        c = RtCounters()
+        self._check(rank, self._lib.rt_get_counters(self.context(rank), C.byref(c)))
+        return c.as_dict()
+
+    def close(self):
+        g, self._group = getattr(self, "_group", None), None
+        if g:
+            self._lib.rt_group_destroy(g)
+
+    def __del__(self):
+        self.close()
+
+
+class _PinnedBlock:
+    def __init__(self, nbytes: int):
+        self.ptr = C.c_void_p()
+        st = _ffi.backend_lib().rt_host_alloc(nbytes, C.byref(self.ptr))
+        if st:
+            raise RtError(st, (_ffi.backend_lib().rt_last_error(None) or b"").decode())
+
+    def __del__(self):
+        ptr, self.ptr = getattr(self, "ptr", None), None
+        if ptr:
+            _ffi.backend_lib().rt_host_free(ptr)
+
+
+def pinned_array(shape, dtype) -> np.ndarray:
+    """A numpy array over page-locked host memory (rt_host_alloc); freed with the array."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    block = _PinnedBlock(max(1, n * dtype.itemsize))
+    raw = (C.c_uint8 * (n * dtype.itemsize)).from_address(block.ptr.value)
+    raw._block = block  # the ctypes view, and through it the array, keep the allocation alive
+    return np.frombuffer(raw, dtype=dtype, count=n).reshape(shape)
 
 
 def write_png(path: str, rgb8: np.ndarray):

@@ -6,7 +6,7 @@
 // the C ABI, the uploads, and two cross-check kernels that are NOT the product path:
 // `render_kernel` / `first_hit_kernel` below walk the reference-layout arrays in the
 // reference's order, one thread per pixel, and count node / primitive tests exactly like the
-// oracle (rt_set_detailed_counters; RT_KERNEL=pixel) — the source of the algorithmic work
+// CPU restatement the tests compare with (rt_set_detailed_counters; RT_KERNEL=pixel) — the source of the algorithmic work
 // figures bench.py reports. RT_KERNEL=wave / fast select the superseded pipelines of
 // rt_wave.cuh / rt_fast.cuh, kept so the tests can check that every kernel agrees bit for bit.
 #include <cuda_fp16.h>
@@ -302,6 +302,13 @@ __global__ void zero_bounce_kernel(float4* accum, size_t count, unsigned long lo
     if (i == 0) atomicAdd(counters, (unsigned long long)count * samples);
 }
 
+// After the sum-reduce of a group: every rank had written alpha = 1, so the root holds the group
+// size there (shader.wgsl:1371 wants 1).
+__global__ void set_alpha_kernel(float4* accum, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) accum[i].w = 1.0f;
+}
+
 __global__ void clear_accum_kernel(float4* accum, size_t count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) accum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -402,20 +409,21 @@ struct RtContext {
     unsigned long long* d_counters = nullptr;
     int sm_count = 0;
     enum Kernel { KERNEL_LOCAL, KERNEL_WAVE, KERNEL_FAST, KERNEL_PIXEL };
-    Kernel kernel = KERNEL_LOCAL;
+    Kernel kernel = KERNEL_WAVE;
     // persistent CTA-local wavefront (rt_local.cuh)
     void* local_arena = nullptr;
     size_t local_arena_bytes = 0;
     uint32_t local_slots = 1024;          // path slots per CTA
     uint32_t local_window = 16;           // samples per window (power of two)
     uint32_t local_stage_paths = 8192;    // parked samples per CTA (ring of windows)
-    bool local_flat_allowed = true;
+    bool local_flat_allowed = false;      // measured: the stack walk is faster (profiles/README.md, r2)
     size_t local_smem_set[2] = {0, 0};    // dynamic shared memory opted in per kernel form
     unsigned long long* d_local_profile = nullptr;  // 11 x u64 (LocalParams::profile)
     // wavefront pipeline state (rt_wave.cuh)
     static constexpr int kMaxGroups = 4;
     rtw::WaveBuffers wave[kMaxGroups]{};
     void* wave_arena = nullptr;
+    size_t wave_arena_bytes = 0;
     uint32_t wave_slots = 0;          // per-group capacity the arena was allocated for
     int wave_arena_groups = 0;
     uint32_t* wave_next_path = nullptr;
@@ -426,7 +434,7 @@ struct RtContext {
     int wave_blocks2[4] = {8, 8, 4, 5};               // ... two groups (measured best: full grids on both streams)
     void* wave_staging = nullptr;     // per-sample radiance planes of the current batch
     size_t wave_staging_bytes = 0;
-    size_t wave_staging_budget = (size_t)8192 << 20;
+    size_t wave_staging_budget = (size_t)8192 << 20;  // upper bound; clamped to what the device has free
     uint32_t* wave_live_host = nullptr;  // pinned read-back of WaveCtrl::live: [2 chunks in flight][groups]
     cudaStream_t wave_streams[kMaxGroups] = {};
     cudaEvent_t wave_events[2][kMaxGroups] = {};
@@ -435,6 +443,8 @@ struct RtContext {
     RtWaveProfile profile{};
     bool detailed = false;
     float first_hit_kernel_ms = 0.f;  // device time of the last rt_first_hit kernel
+    void* d_first_hit = nullptr;      // slot map, then distance map, of rt_first_hit
+    size_t first_hit_capacity = 0;    // pixels
     uint64_t launches = 0;
 };
 
@@ -550,7 +560,9 @@ int wave_reserve(RtContext* ctx, uint32_t slots, int groups, size_t staging_byte
         const size_t S = slots;
         // per group: 3 x 32-byte pair arrays + 2 x 16 + fb (8) + rayq (4 x 4) + occl (1) + stage (1) + ctrl
         const size_t per_group = (S * (3 * 32 + 2 * 16 + 8 + 16 + 2) + 1024 + 255) & ~(size_t)255;
+        ctx->wave_arena_bytes = 0;
         RT_CUDA(ctx, cudaMalloc(&ctx->wave_arena, per_group * (size_t)groups + 256));
+        ctx->wave_arena_bytes = per_group * (size_t)groups + 256;
         for (int g = 0; g < groups; g++) {
             char* q = (char*)ctx->wave_arena + per_group * (size_t)g;
             rtw::WaveBuffers& b = ctx->wave[g];
@@ -606,8 +618,21 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
 
     // Batch size: as many samples as the staging budget holds, and path indices must fit 32 bits.
     const size_t pixels = (size_t)ctx->width * ctx->height;
-    uint64_t batch = ctx->wave_staging_budget / (pixels * sizeof(float4));
-    const uint64_t index_cap = 0xFFFF0000ull / base.pixel_ids;
+    // The staging planes must fit what the device has left (the budget is only an upper bound).
+    size_t budget = ctx->wave_staging_budget;
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t usable = free_b + ctx->wave_staging_bytes;  // our own planes are reusable
+            const size_t reserve = (size_t)2048 << 20;               // slot arena + headroom for the caller
+            const size_t cap = usable > reserve ? (usable - reserve) / 4 * 3 : usable / 2;
+            if (budget > cap) budget = cap;
+        }
+    }
+    uint64_t batch = budget / (pixels * sizeof(float4));
+    // Every slot that retires after the paths ran out still bumps next_path once per wave it
+    // waits: leave that much headroom below 2^32.
+    const uint64_t index_cap = (0xFFFFFFFFull - 64ull * ctx->wave_max_slots) / base.pixel_ids;
     if (batch > index_cap) batch = index_cap;
     if (batch > sample_count) batch = sample_count;
     if (batch < 1) batch = 1;
@@ -1014,6 +1039,7 @@ int rt_create(int device, RtContext** out) {
         if (!strcmp(k, "pixel")) ctx->kernel = RtContext::KERNEL_PIXEL;
         else if (!strcmp(k, "fast")) ctx->kernel = RtContext::KERNEL_FAST;
         else if (!strcmp(k, "wave")) ctx->kernel = RtContext::KERNEL_WAVE;
+        else if (!strcmp(k, "local")) ctx->kernel = RtContext::KERNEL_LOCAL;
     }
     if (const char* k = getenv("RT_LOCAL_SLOTS")) {
         long v = atol(k);
@@ -1075,6 +1101,7 @@ void rt_destroy(RtContext* ctx) {
     cudaFree(ctx->wave_arena);
     cudaFree(ctx->local_arena);
     cudaFree(ctx->d_local_profile);
+    cudaFree(ctx->d_first_hit);
     if (ctx->wave_live_host) cudaFreeHost(ctx->wave_live_host);
     cudaFree(ctx->wave_staging);
     for (int g = 0; g < RtContext::kMaxGroups; g++) {
@@ -1190,64 +1217,85 @@ int rt_upload_scene(RtContext* ctx, const RtSceneDesc* s) {
     for (uint32_t i = 0; i < s->plane_count; i++)
         write_plane((size_t)slots + s->sphere_count + i, s->planes[i]);
 
-    // ---- upload ----
-    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    free_scene(ctx);
-    float* d_raw_materials = nullptr;
-    RT_CUDA(ctx, cudaMalloc(&ctx->d_nodes, nodes.size() * sizeof(float4)));
-    RT_CUDA(ctx, cudaMalloc(&ctx->d_records, records.size() * sizeof(float4)));
-    RT_CUDA(ctx, cudaMalloc(&ctx->d_tri_normals, tri_normals.size() * sizeof(float4)));
-    RT_CUDA(ctx, cudaMalloc(&ctx->d_materials, (size_t)s->material_count * 3 * sizeof(float4)));
-    RT_CUDA(ctx, cudaMalloc(&d_raw_materials, (size_t)s->material_count * sizeof(RtMaterial)));
-    RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_nodes, nodes.data(), nodes.size() * sizeof(float4),
-                                 cudaMemcpyHostToDevice, ctx->stream));
-    RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_records, records.data(), records.size() * sizeof(float4),
-                                 cudaMemcpyHostToDevice, ctx->stream));
-    RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tri_normals, tri_normals.data(),
-                                 tri_normals.size() * sizeof(float4), cudaMemcpyHostToDevice,
-                                 ctx->stream));
-    RT_CUDA(ctx, cudaMemcpyAsync(d_raw_materials, s->materials,
-                                 (size_t)s->material_count * sizeof(RtMaterial),
-                                 cudaMemcpyHostToDevice, ctx->stream));
-    {
-        if (slots >= rtf::kLeafSlotMask)
-            return fail(ctx, RT_ERR_INVALID_ARGUMENT, "too many primitives (%u) for the 26-bit leaf slot field", slots);
-        rtf::FastLayout fl;
-        rtf::build_fast_layout(*s, fl);
-        RT_CUDA(ctx, cudaMalloc(&ctx->d_n2, fl.n2.size() * sizeof(float4)));
-        RT_CUDA(ctx, cudaMalloc(&ctx->d_tri, (fl.tri.size() + 1) * sizeof(float4)));
-        RT_CUDA(ctx, cudaMalloc(&ctx->d_ana, fl.ana.size() * sizeof(float4)));
-        RT_CUDA(ctx, cudaMalloc(&ctx->d_pre, fl.pre.size() * sizeof(float4)));
-        RT_CUDA(ctx, cudaMemcpy(ctx->d_n2, fl.n2.data(), fl.n2.size() * sizeof(float4), cudaMemcpyHostToDevice));
-        if (!fl.tri.empty())
-            RT_CUDA(ctx, cudaMemcpy(ctx->d_tri, fl.tri.data(), fl.tri.size() * sizeof(float4), cudaMemcpyHostToDevice));
-        RT_CUDA(ctx, cudaMemcpy(ctx->d_ana, fl.ana.data(), fl.ana.size() * sizeof(float4), cudaMemcpyHostToDevice));
-        RT_CUDA(ctx, cudaMemcpy(ctx->d_pre, fl.pre.data(), fl.pre.size() * sizeof(float4), cudaMemcpyHostToDevice));
-        RT_CUDA(ctx, cudaMalloc(&ctx->d_flat, fl.flat.size() * sizeof(float4)));
-        RT_CUDA(ctx, cudaMemcpy(ctx->d_flat, fl.flat.data(), fl.flat.size() * sizeof(float4), cudaMemcpyHostToDevice));
-        if (!fl.big_len.empty()) {
-            RT_CUDA(ctx, cudaMalloc(&ctx->d_big_len, fl.big_len.size() * sizeof(uint32_t)));
-            RT_CUDA(ctx, cudaMemcpy(ctx->d_big_len, fl.big_len.data(), fl.big_len.size() * sizeof(uint32_t),
-                                    cudaMemcpyHostToDevice));
+    if (slots >= rtf::kLeafSlotMask)
+        return fail(ctx, RT_ERR_INVALID_ARGUMENT, "too many primitives (%u) for the 26-bit leaf slot field", slots);
+    rtf::FastLayout fl;
+    rtf::build_fast_layout(*s, fl);
+
+    // ---- upload: into fresh buffers; the scene in use is replaced only when all of it is there ----
+    struct Pending {
+        std::vector<void*> owned;
+        ~Pending() {
+            for (void* q : owned) cudaFree(q);
         }
-        RT_CUDA(ctx, cudaMalloc(&ctx->d_ana_paths, fl.ana_paths.size() * sizeof(uint32_t)));
-        RT_CUDA(ctx, cudaMemcpy(ctx->d_ana_paths, fl.ana_paths.data(), fl.ana_paths.size() * sizeof(uint32_t),
-                                cudaMemcpyHostToDevice));
-        ctx->fast = fl.view;
-        ctx->fast.n2 = ctx->d_n2;
-        ctx->fast.tri = ctx->d_tri;
-        ctx->fast.ana = ctx->d_ana;
-        ctx->fast.pre = ctx->d_pre;
-        ctx->fast.flat = ctx->d_flat;
-        ctx->fast.big_len = ctx->d_big_len;
-        ctx->fast.ana_paths = ctx->d_ana_paths;
+    } pending;
+    cudaError_t up_err = cudaSuccess;
+    auto upload = [&](const void* src, size_t bytes, size_t alloc_bytes) -> void* {
+        if (up_err != cudaSuccess) return nullptr;
+        void* d = nullptr;
+        up_err = cudaMalloc(&d, alloc_bytes ? alloc_bytes : 16);
+        if (up_err != cudaSuccess) return nullptr;
+        pending.owned.push_back(d);
+        if (bytes) up_err = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        return d;
+    };
+    auto up4 = [&](const std::vector<float4>& v, size_t extra = 0) {
+        return (float4*)upload(v.data(), v.size() * sizeof(float4), (v.size() + extra) * sizeof(float4));
+    };
+    float4* n_nodes = up4(nodes);
+    float4* n_records = up4(records);
+    float4* n_tri_normals = up4(tri_normals);
+    float4* n_materials = (float4*)upload(nullptr, 0, (size_t)s->material_count * 3 * sizeof(float4));
+    float* d_raw_materials = (float*)upload(s->materials, (size_t)s->material_count * sizeof(RtMaterial),
+                                            (size_t)s->material_count * sizeof(RtMaterial));
+    float4* n_n2 = up4(fl.n2);
+    float4* n_tri = up4(fl.tri, 1);
+    float4* n_ana = up4(fl.ana);
+    float4* n_pre = up4(fl.pre);
+    float4* n_flat = up4(fl.flat);
+    uint32_t* n_big_len = fl.big_len.empty() ? nullptr
+                                             : (uint32_t*)upload(fl.big_len.data(), fl.big_len.size() * sizeof(uint32_t),
+                                                                 fl.big_len.size() * sizeof(uint32_t));
+    uint32_t* n_ana_paths = (uint32_t*)upload(fl.ana_paths.data(), fl.ana_paths.size() * sizeof(uint32_t),
+                                              fl.ana_paths.size() * sizeof(uint32_t));
+    if (up_err == cudaSuccess) {
+        bake_materials_kernel<<<(s->material_count + 127) / 128, 128, 0, ctx->stream>>>(
+            d_raw_materials, n_materials, s->material_count);
+        ctx->launches++;
+        up_err = cudaGetLastError();
     }
-    bake_materials_kernel<<<(s->material_count + 127) / 128, 128, 0, ctx->stream>>>(
-        d_raw_materials, ctx->d_materials, s->material_count);
-    ctx->launches++;
-    RT_CUDA(ctx, cudaGetLastError());
-    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_raw_materials);
+    // also waits for the renders still using the old scene
+    if (up_err == cudaSuccess) up_err = cudaStreamSynchronize(ctx->stream);
+    if (up_err != cudaSuccess)
+        return fail(ctx, up_err == cudaErrorMemoryAllocation ? RT_ERR_OUT_OF_MEMORY : RT_ERR_CUDA,
+                    "scene upload failed: %s (the previous scene is still in place)", cudaGetErrorString(up_err));
+
+    free_scene(ctx);
+    for (void*& q : pending.owned)
+        if (q == (void*)d_raw_materials) {
+            cudaFree(q);
+            q = nullptr;
+        }
+    pending.owned.clear();  // the context owns the rest now
+    ctx->d_nodes = n_nodes;
+    ctx->d_records = n_records;
+    ctx->d_tri_normals = n_tri_normals;
+    ctx->d_materials = n_materials;
+    ctx->d_n2 = n_n2;
+    ctx->d_tri = n_tri;
+    ctx->d_ana = n_ana;
+    ctx->d_pre = n_pre;
+    ctx->d_flat = n_flat;
+    ctx->d_big_len = n_big_len;
+    ctx->d_ana_paths = n_ana_paths;
+    ctx->fast = fl.view;
+    ctx->fast.n2 = ctx->d_n2;
+    ctx->fast.tri = ctx->d_tri;
+    ctx->fast.ana = ctx->d_ana;
+    ctx->fast.pre = ctx->d_pre;
+    ctx->fast.flat = ctx->d_flat;
+    ctx->fast.big_len = ctx->d_big_len;
+    ctx->fast.ana_paths = ctx->d_ana_paths;
 
     ctx->scene.nodes = ctx->d_nodes;
     ctx->scene.records = ctx->d_records;
@@ -1331,7 +1379,9 @@ int rt_clear(RtContext* ctx) {
 
 int rt_resize(RtContext* ctx, uint32_t width, uint32_t height) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
-    if (!width || !height || (uint64_t)width * height > 0x7FFFFFFFull)
+    // pixel ids are handed out per 8x8 tile, partial tiles included: they must fit 31 bits too
+    const uint64_t tile_ids = (((uint64_t)width + 7u) / 8u) * (((uint64_t)height + 7u) / 8u) * 64u;
+    if (!width || !height || (uint64_t)width * height > 0x7FFFFFFFull || tile_ids > 0x7FFFFFFFull)
         return fail(ctx, RT_ERR_INVALID_ARGUMENT, "invalid resolution %ux%u", width, height);
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1443,14 +1493,18 @@ int rt_first_hit(RtContext* ctx, uint32_t sample_index, uint32_t* slot_out, floa
     if (st != RT_OK) return st;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     size_t count = (size_t)ctx->width * ctx->height;
-    uint32_t* d_slot = nullptr;
-    float* d_t = nullptr;
-    RT_CUDA(ctx, cudaMalloc(&d_slot, count * 4));
-    cudaError_t e = cudaMalloc(&d_t, count * 4);
-    if (e != cudaSuccess) {
-        cudaFree(d_slot);
-        return fail(ctx, RT_ERR_OUT_OF_MEMORY, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    // The two device maps live as long as the context (re-allocated when the frame grows).
+    if (ctx->first_hit_capacity < count) {
+        RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_first_hit);
+        ctx->d_first_hit = nullptr;
+        ctx->first_hit_capacity = 0;
+        RT_CUDA(ctx, cudaMalloc(&ctx->d_first_hit, count * 8));
+        ctx->first_hit_capacity = count;
     }
+    uint32_t* d_slot = (uint32_t*)ctx->d_first_hit;
+    float* d_t = (float*)ctx->d_first_hit + count;
+    cudaError_t e = cudaSuccess;
     FirstHitParams p;
     p.scene = ctx->scene;
     p.camera = ctx->camera;
@@ -1489,11 +1543,24 @@ int rt_first_hit(RtContext* ctx, uint32_t sample_index, uint32_t* slot_out, floa
         e = cudaMemcpyAsync(t_out, d_t, count * 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) cudaEventElapsedTime(&ctx->first_hit_kernel_ms, ctx->ev_start, ctx->ev_stop);
-    cudaFree(d_slot);
-    cudaFree(d_t);
     if (e != cudaSuccess)
         return fail(ctx, RT_ERR_CUDA, "first-hit pass failed: %s", cudaGetErrorString(e));
     return RT_OK;
+}
+
+// Page-locked host memory for the caller's output buffers: the device -> host copies of
+// rt_first_hit / rt_read_accum then run at link speed instead of through a bounce buffer.
+int rt_host_alloc(size_t bytes, void** out) {
+    if (!out || !bytes) return RT_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess)
+        return fail(nullptr, RT_ERR_OUT_OF_MEMORY, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return RT_OK;
+}
+
+void rt_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 int rt_sync(RtContext* ctx) {
@@ -1558,6 +1625,28 @@ int rt_set_profiling(RtContext* ctx, int enabled) {
 int rt_get_profile(RtContext* ctx, RtWaveProfile* out) {
     if (!ctx || !out) return RT_ERR_INVALID_ARGUMENT;
     *out = ctx->profile;
+    return RT_OK;
+}
+
+int rt_set_memory_budget(RtContext* ctx, uint64_t staging_bytes, uint32_t path_slots) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (staging_bytes) {
+        if (staging_bytes < ((uint64_t)1 << 20)) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "staging budget below 1 MiB");
+        ctx->wave_staging_budget = (size_t)staging_bytes;
+    }
+    if (path_slots) {
+        if (path_slots < 1024u || path_slots > (1u << 24))
+            return fail(ctx, RT_ERR_INVALID_ARGUMENT, "path slot count %u outside [1024, 2^24]", path_slots);
+        ctx->wave_max_slots = path_slots;
+    }
+    return RT_OK;
+}
+
+int rt_get_memory_usage(RtContext* ctx, uint64_t* bytes) {
+    if (!ctx || !bytes) return RT_ERR_INVALID_ARGUMENT;
+    *bytes = (uint64_t)ctx->wave_staging_bytes + (uint64_t)ctx->wave_arena_bytes + (uint64_t)ctx->local_arena_bytes +
+             (uint64_t)ctx->first_hit_capacity * 8u +
+             (ctx->d_accum_own ? (uint64_t)ctx->width * ctx->height * sizeof(float4) : 0u);
     return RT_OK;
 }
 
@@ -1630,6 +1719,7 @@ namespace {
 
 struct NcclApi {
     void* handle = nullptr;
+    std::string load_error;  // dlerror() text of the failed dlopen (dlerror clears itself when read)
     ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t,
@@ -1646,7 +1736,11 @@ NcclApi& nccl_api() {
     std::call_once(once, [] {
         api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-        if (!api.handle) return;
+        if (!api.handle) {
+            const char* e = dlerror();
+            api.load_error = e ? e : "dlopen failed";
+            return;
+        }
         api.CommInitAll = (decltype(api.CommInitAll))dlsym(api.handle, "ncclCommInitAll");
         api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
         api.Reduce = (decltype(api.Reduce))dlsym(api.handle, "ncclReduce");
@@ -1655,6 +1749,7 @@ NcclApi& nccl_api() {
         api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
         api.ok = api.CommInitAll && api.CommDestroy && api.Reduce && api.GroupStart &&
                  api.GroupEnd && api.GetErrorString;
+        if (!api.ok) api.load_error = "missing symbols";
     });
     return api;
 }
@@ -1685,8 +1780,7 @@ int rt_group_create(int count, const int* devices, RtGroup** out) {
         NcclApi& api = nccl_api();
         if (!api.ok) {
             rt_group_destroy(g);
-            return fail(nullptr, RT_ERR_NCCL, "libnccl.so.2 could not be loaded: %s",
-                        dlerror() ? dlerror() : "missing symbols");
+            return fail(nullptr, RT_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", api.load_error.c_str());
         }
         g->comms.resize((size_t)count);
         ncclResult_t r = api.CommInitAll(g->comms.data(), count, devices);
@@ -1755,6 +1849,19 @@ int rt_group_reduce(RtGroup* g, int root) {
     if (r == ncclSuccess) r = r2;
     if (r != ncclSuccess)
         return fail(r0, RT_ERR_NCCL, "ncclReduce failed: %s", api.GetErrorString(r));
+    // Post-conditions (rt_backend.h): the root holds the sum with alpha = 1; every other rank's
+    // buffer is zero again, so a further rt_group_render + rt_group_reduce round adds only its
+    // own samples (progressive accumulation, one round per batch of frames).
+    const size_t count = floats / 4;
+    for (size_t i = 0; i < g->ctxs.size(); i++) {
+        RtContext* c = g->ctxs[i];
+        cudaSetDevice(c->device);
+        if ((int)i == root) set_alpha_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(c->d_accum, count);
+        else clear_accum_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(c->d_accum, count);
+        c->launches++;
+        cudaError_t ce = cudaGetLastError();
+        if (ce != cudaSuccess) return fail(r0, RT_ERR_CUDA, "post-reduce kernel failed: %s", cudaGetErrorString(ce));
+    }
     return RT_OK;
 }
 
