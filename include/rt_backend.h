@@ -113,6 +113,17 @@ int rt_write_accum(RtContext* ctx, const float* rgba_in);
  * sRGB encode (surface format, src/hdr.rs:120). rgb8_out is W*H*3 host bytes. */
 int rt_tonemap_rgb8(RtContext* ctx, uint32_t sample_total, uint8_t* rgb8_out);
 
+/* The reference's dev_index views (keys 2 and 3, src/camera.rs:279-285; shader.wgsl:1314-1338):
+ * the contents of out_texture (rgba16float, W*H*4 floats here) after one dispatch with that
+ * dev_index, for the frame whose sample_count uniform is `sample_index`.
+ *   2: where the environment's alias table sends samples — every pixel draws 20 texels and adds
+ *      0.1 / 20 at their coordinates. The shader's read-modify-write races between invocations;
+ *      this applies every draw (a race-free execution of the same code).
+ *   3: the environment's texels at the pixel's own coordinates, saturated.
+ * Any other dev_index renders normally in the reference and is refused here (use rt_render). */
+int rt_debug_view(RtContext* ctx, uint32_t dev_index, uint32_t environment_index, uint32_t sample_index,
+                  float* rgba_out);
+
 /* Per-kernel device time of the wavefront pipeline (CUDA events around every launch on the
  * launching stream), accumulated over rt_render calls while profiling is enabled. Kernel
  * order: shade, finish, pre-pass, walk (rsoderh-raytracing_b200/csrc/rt_wave.cuh). */

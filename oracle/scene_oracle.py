@@ -68,6 +68,12 @@ class Bounds3:
 
 
 # ---------------------------------------------------------------- OBJ (mesh.rs + wavefront_obj)
+# wavefront_obj 11.0.0 is not under /root/reference; its fan triangulation is restated from memory as
+# anchored at the LAST corner. tools/fan_anchor_report.py flips this switch to measure what would
+# change if the crate anchored at the first corner instead (tests/golden/fan_anchor_report.json).
+FAN_ANCHOR = "last"
+
+
 def load_obj(text: str):
     """Returns (vertices [n,3] f32, normals [m,3] f32, triangles [(v0,v1,v2,n0,n1,n2)])."""
     verts, norms, faces = [], [], []
@@ -92,9 +98,11 @@ def load_obj(text: str):
         n = len(corners)
         if n < 3:
             continue
-        last = corners[-1]
-        for i in range(n - 2):  # fan anchored at the LAST corner (wavefront_obj)
-            a, b, c = last, corners[i], corners[i + 1]
+        for i in range(n - 2):
+            if FAN_ANCHOR == "last":  # fan anchored at the LAST corner (wavefront_obj)
+                a, b, c = corners[-1], corners[i], corners[i + 1]
+            else:
+                a, b, c = corners[0], corners[i + 1], corners[i + 2]
             if a[1] is None or b[1] is None or c[1] is None:
                 raise ValueError("Object must include baked normals")
 

@@ -164,6 +164,7 @@ BACKEND_SIGNATURES = {
     "rt_render": (C.c_int, [_vp, _u32, _u32, _u32, _u32]),
     "rt_first_hit": (C.c_int, [_vp, _u32, _vp, _vp]),
     "rt_first_hit_kernel_ms": (C.c_float, [_vp]),
+    "rt_debug_view": (C.c_int, [_vp, _u32, _u32, _u32, _vp]),
     "rt_set_memory_budget": (C.c_int, [_vp, C.c_uint64, _u32]),
     "rt_get_memory_usage": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "rt_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),

@@ -432,6 +432,20 @@ class State:
         return out
 
     # -- counters / timing / interop --
+    def debug_view(self, dev_index: int, sample_index: int = 0) -> np.ndarray:
+        """out_texture of the reference's dev_index 2 / 3 views (shader.wgsl:1314-1338)."""
+        out = np.empty((self.height, self.width, 4), dtype=np.float32)
+        self._check(self._lib.rt_debug_view(self._ctx, dev_index, self.environment_index, sample_index,
+                                            out.ctypes.data))
+        return out
+
+    def next_environment(self):
+        """The `next_environment` key (camera.rs:271-278): cycle the slot, restart accumulation."""
+        self.environment_index += 1
+        if self.environment_index >= len(self.environments.environments):
+            self.environment_index = 0
+        self.reset()
+
     def set_memory_budget(self, staging_bytes: int = 0, path_slots: int = 0):
         """rt_set_memory_budget: upper bounds of the staging planes / path-slot arena (0 keeps)."""
         self._check(self._lib.rt_set_memory_budget(self._ctx, staging_bytes, path_slots))

@@ -352,6 +352,52 @@ __global__ void tonemap_kernel(const float4* accum, uint8_t* rgb8, size_t count,
     }
 }
 
+// dev_index views of `main` (shader.wgsl:1314-1338): they write out_texture (rgba16float, cleared
+// to zero every frame, state.rs:797-800) and return before any ray is cast.
+//   2: every invocation draws 20 texels from the environment's alias table and adds 0.1 / 20 to
+//      out_texture at the texel's coordinates. The shader's load + store pairs of different
+//      invocations race; here every draw is applied (what a race-free execution gives): count the
+//      draws per texel, then replay that many f16-rounded additions.
+//   3: out_texture = saturate(environment texel at the pixel's own coordinates).
+__global__ void view_distribution_count_kernel(EnvView env, uint32_t width, uint32_t height, uint32_t sample,
+                                               uint32_t* counts) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    uint32_t rng = rng_seed(y * width + x, sample);
+    const uint32_t length = env.width * env.height;
+    for (int i = 0; i < 20; i++) {
+        // random_index_in_environment (shader.wgsl:689-706)
+        uint32_t index = min((uint32_t)(rng_uniform(rng) * (float)length), length - 1u);
+        float4 entry = env.alias[index];
+        uint32_t pick = rng_uniform(rng) < entry.x ? index : f_as_u(entry.y);
+        uint32_t ex = pick % env.width, ey = pick / env.width;
+        if (ex < width && ey < height) atomicAdd(&counts[ey * width + ex], 1u);  // stores outside the texture are dropped
+    }
+}
+
+__global__ void view_distribution_resolve_kernel(const uint32_t* counts, float4* out, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float step = 0.1f / 20.0f;  // vec3(0.1) / f32(count)
+    float c = 0.0f;
+    for (uint32_t k = counts[i]; k > 0u; k--) {
+        float next = __half2float(__float2half_rn(c + step));
+        if (next == c) break;  // the f16 texel has stopped growing
+        c = next;
+    }
+    out[i] = make_float4(c, c, c, 0.0f);
+}
+
+__global__ void view_environment_kernel(EnvView env, uint32_t width, uint32_t height, float4* out) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);  // textureLoad outside the texture: zero
+    if (x < env.width && y < env.height) t = env.texels[(size_t)y * env.width + x];
+    out[(size_t)y * width + x] = make_float4(__half2float(__float2half_rn(saturate(t.x))),
+                                             __half2float(__float2half_rn(saturate(t.y))),
+                                             __half2float(__float2half_rn(saturate(t.z))), 0.0f);
+}
+
 // =====================================================================================
 // Host side
 // =====================================================================================
@@ -413,9 +459,9 @@ struct RtContext {
     // persistent CTA-local wavefront (rt_local.cuh)
     void* local_arena = nullptr;
     size_t local_arena_bytes = 0;
-    uint32_t local_slots = 1024;          // path slots per CTA
-    uint32_t local_window = 16;           // samples per window (power of two)
-    uint32_t local_stage_paths = 8192;    // parked samples per CTA (ring of windows)
+    uint32_t local_slots = 128;           // path slots per warp
+    uint32_t local_window = 4;            // samples per window (power of two)
+    uint32_t* local_error_word = nullptr; // device word a stalled warp sets (rt_local.cuh)
     bool local_flat_allowed = false;      // measured: the stack walk is faster (profiles/README.md, r2)
     size_t local_smem_set[2] = {0, 0};    // dynamic shared memory opted in per kernel form
     unsigned long long* d_local_profile = nullptr;  // 11 x u64 (LocalParams::profile)
@@ -849,38 +895,46 @@ int local_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin,
     p.counters = ctx->d_counters;
     p.width = ctx->width;
     p.height = ctx->height;
-    p.tiles_x = (ctx->width + 7u) / 8u;
-    p.tiles_total = p.tiles_x * ((ctx->height + 7u) / 8u);
     p.sample_begin = sample_begin;
     p.sample_count = sample_count;
     p.max_bounces = max_bounces;
+
+    const uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)rtl::kMinBlocks;
+    const uint32_t warps = grid * (uint32_t)rtl::kWarps;
+    // Tiles are the unit of load balance: 8x4 pixels, 4x4 when the frame has few of them.
+    p.tile_w_shift = 3u;
+    p.tile_shift = 5u;
+    if ((uint64_t)((ctx->width + 7u) / 8u) * ((ctx->height + 3u) / 4u) < 4ull * warps) {
+        p.tile_w_shift = 2u;
+        p.tile_shift = 4u;
+    }
+    const uint32_t tile_w = 1u << p.tile_w_shift, tile_h = (1u << p.tile_shift) >> p.tile_w_shift;
+    p.tiles_x = (ctx->width + tile_w - 1u) / tile_w;
+    p.tiles_total = p.tiles_x * ((ctx->height + tile_h - 1u) / tile_h);
 
     const bool flat = ctx->local_flat_allowed && ctx->fast.flat_leaves > 0u;
     const uint32_t window = floor_pow2(sample_count < ctx->local_window ? sample_count : ctx->local_window);
     uint32_t shift = 0;
     while ((1u << shift) < window) shift++;
     p.window_shift = shift;
-    uint32_t ring = floor_pow2(ctx->local_stage_paths / (64u * window) > 0u ? ctx->local_stage_paths / (64u * window) : 1u);
-    if (ring > rtl::kRing) ring = rtl::kRing;
-    p.ring_entries = ring;
+    p.ring_entries = rtl::kRing;
+    p.slots = ctx->local_slots;
+    p.qcap = 32u;
+    while (p.qcap < p.slots) p.qcap *= 2u;
     // few samples per tile: take several tiles per atomic so that one grab feeds the slots once
-    const uint64_t per_tile = 64ull * sample_count;
-    uint32_t grab = (uint32_t)((ctx->local_slots + per_tile - 1) / per_tile);
+    const uint64_t per_tile = (uint64_t)(1u << p.tile_shift) * sample_count;
+    uint32_t grab = (uint32_t)((p.slots + per_tile - 1) / per_tile);
     p.tile_grab = grab < 1u ? 1u : (grab > 64u ? 64u : grab);
 
-    // no more CTAs than tiles, no more slots than a CTA's share of the paths needs
-    const uint32_t grid_full = (uint32_t)ctx->sm_count * (uint32_t)rtl::kMinBlocks;
-    const uint32_t grid = p.tiles_total < grid_full ? p.tiles_total : grid_full;
-    p.slots = ctx->local_slots;
-
-    const size_t T = (size_t)grid_full * p.slots;
-    const size_t stage_f4 = (size_t)grid_full * ((size_t)ring * window * 64u);
-    // rOD 32 + pTLPI 64 + sray_d 16 + hit 16 + fb 8 + occl 1 per slot, staging, tile counter
+    const size_t T = (size_t)warps * p.slots;
+    const size_t stage_f4 = (size_t)warps * (((size_t)p.ring_entries << shift) << p.tile_shift);
+    // rOD 32 + pTLPI 64 + sray_d 16 + hit 16 + fb 8 + occl 1 per slot, staging, tile counter + error word
     const size_t bytes = T * (32 + 64 + 16 + 16 + 8 + 1) + 256 + stage_f4 * sizeof(float4) + 256;
     if (!ctx->local_arena || ctx->local_arena_bytes < bytes) {
         RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->local_arena);
         ctx->local_arena = nullptr;
+        ctx->local_error_word = nullptr;
         ctx->local_arena_bytes = 0;
         RT_CUDA(ctx, cudaMalloc(&ctx->local_arena, bytes));
         ctx->local_arena_bytes = bytes;
@@ -893,10 +947,12 @@ int local_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin,
         p.hit = (float4*)q;     q += T * 16;
         p.staging = (float4*)q; q += stage_f4 * sizeof(float4);
         p.fb = (float2*)q;      q += T * 8;
-        p.next_tile = (uint32_t*)q; q += 256;
+        p.next_tile = (uint32_t*)q;
+        p.error = (uint32_t*)q + 1; q += 256;
         p.occl = (uint8_t*)q;
     }
-    const size_t smem = rtl::smem_layout(p.scene, p.slots, flat).bytes;
+    ctx->local_error_word = p.error;
+    const size_t smem = rtl::smem_layout(p.scene, p.slots, p.qcap, flat).bytes;
     if (ctx->local_smem_set[flat ? 1 : 0] < smem) {
         cudaError_t ce = flat ? cudaFuncSetAttribute(rtl::local_wave_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                               : cudaFuncSetAttribute(rtl::local_wave_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -904,12 +960,13 @@ int local_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin,
             return fail(ctx, RT_ERR_CUDA, "%zu bytes of shared memory per CTA refused: %s", smem, cudaGetErrorString(ce));
         ctx->local_smem_set[flat ? 1 : 0] = smem;
     }
-    RT_CUDA(ctx, cudaMemsetAsync(p.next_tile, 0, sizeof(uint32_t), ctx->stream));
+    RT_CUDA(ctx, cudaMemsetAsync(p.next_tile, 0, 2 * sizeof(uint32_t), ctx->stream));
     static const bool timeline_print = getenv("RT_LOCAL_PROFILE") != nullptr;
     const bool profiling = ctx->profiling || timeline_print;
+    constexpr int kProfileWords = 14;
     if (profiling) {
-        if (!ctx->d_local_profile) RT_CUDA(ctx, cudaMalloc(&ctx->d_local_profile, 11 * sizeof(unsigned long long)));
-        RT_CUDA(ctx, cudaMemsetAsync(ctx->d_local_profile, 0, 11 * sizeof(unsigned long long), ctx->stream));
+        if (!ctx->d_local_profile) RT_CUDA(ctx, cudaMalloc(&ctx->d_local_profile, kProfileWords * sizeof(unsigned long long)));
+        RT_CUDA(ctx, cudaMemsetAsync(ctx->d_local_profile, 0, kProfileWords * sizeof(unsigned long long), ctx->stream));
         p.profile = ctx->d_local_profile;
         RT_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
     }
@@ -919,9 +976,9 @@ int local_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin,
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "render kernel launch failed: %s", cudaGetErrorString(ce));
     if (profiling) {
-        // Phase shares of the one launch (clock64 per CTA, thread 0, at the barriers) scaled to its
+        // Stage shares of the one launch (clock64 per warp, lane 0, around every batch) scaled to its
         // CUDA-event duration. Profiling makes the call synchronous.
-        unsigned long long h[11];
+        unsigned long long h[kProfileWords];
         float ms = 0.f;
         RT_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
         RT_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_local_profile, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
@@ -931,25 +988,23 @@ int local_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin,
         double cyc = 0;
         for (int i = 0; i < 5; i++) cyc += (double)h[i];
         if (cyc <= 0) cyc = 1;
-        const double ctas = h[10] ? (double)h[10] : 1.0;
         // kernel order of RtWaveProfile: shade, finish, pre-pass, walk; bookkeeping goes to gap_ms
-        const int order[4] = {0, 2, 3, 4};
         ctx->profile.renders++;
-        ctx->profile.waves += (uint64_t)((double)h[9] / ctas + 0.5);
         for (int j = 0; j < 4; j++) {
             ctx->profile.launches[j] += 1;
-            ctx->profile.kernel_ms[j] += ms * (double)h[order[j]] / cyc;
+            ctx->profile.kernel_ms[j] += ms * (double)h[j] / cyc;
         }
-        ctx->profile.gap_ms += ms * (double)h[1] / cyc;
+        ctx->profile.gap_ms += ms * (double)h[4] / cyc;
         ctx->profile.total_ms += ms;
         if (timeline_print) {
-            const double w = h[9] ? (double)h[9] : 1.0;
-            fprintf(stderr, "[local profile] %s walk, %u CTAs x %u slots, window %u x ring %u: %.3f ms, %.0f waves per CTA, "
-                    "%.1f us per wave | shade %.1f%% book %.1f%% finish %.1f%% prepass %.1f%% walk %.1f%% | items per wave: "
-                    "shade %.0f finish %.0f rays %.0f walk %.0f\n",
-                    flat ? "flat" : "stack", grid, p.slots, window, ring, ms, (double)h[9] / ctas, ms * 1e3 / ((double)h[9] / ctas),
+            auto per = [&](int j) { return h[9 + j] ? (double)h[5 + j] / (double)h[9 + j] : 0.0; };
+            fprintf(stderr, "[local profile] %s walk, %u warps x %u slots, tile %ux%u, window %u x ring %u: %.3f ms | shade %.1f%% "
+                    "finish %.1f%% prepass %.1f%% walk %.1f%% book %.1f%% | items per batch: shade %.1f finish %.1f "
+                    "prepass %.1f walk %.1f | batches per warp: %.0f %.0f %.0f %.0f\n",
+                    flat ? "flat" : "stack", warps, p.slots, tile_w, tile_h, window, p.ring_entries, ms,
                     100.0 * h[0] / cyc, 100.0 * h[1] / cyc, 100.0 * h[2] / cyc, 100.0 * h[3] / cyc, 100.0 * h[4] / cyc,
-                    h[5] / w, h[6] / w, h[7] / w, h[8] / w);
+                    per(0), per(1), per(2), per(3), (double)h[9] / warps, (double)h[10] / warps, (double)h[11] / warps,
+                    (double)h[12] / warps);
         }
     }
     return RT_OK;
@@ -975,6 +1030,18 @@ cudaError_t launch_first_hit(const FirstHitParams& p, uint32_t depth, cudaStream
     else if (depth <= 32) first_hit_kernel<COUNT, 32><<<grid, block, 0, stream>>>(p);
     else first_hit_kernel<COUNT, 64><<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
+}
+
+// After a stream synchronisation: did a warp of the persistent render kernel give up (its
+// scheduler found no work although paths were outstanding)? Never seen; it turns a would-be hang
+// into an error.
+int check_render_error(RtContext* ctx) {
+    if (!ctx->local_error_word) return RT_OK;
+    uint32_t flag = 0;
+    RT_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->local_error_word, sizeof flag, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flag) return fail(ctx, RT_ERR_CUDA, "the render kernel stalled with paths outstanding (internal error)");
+    return RT_OK;
 }
 
 int check_ready(RtContext* ctx, uint32_t env_index, bool need_env) {
@@ -1043,15 +1110,11 @@ int rt_create(int device, RtContext** out) {
     }
     if (const char* k = getenv("RT_LOCAL_SLOTS")) {
         long v = atol(k);
-        if (v >= 64 && v <= (long)rtl::kMaxSlots) ctx->local_slots = (uint32_t)v;
+        if (v >= 32 && v <= (long)rtl::kMaxSlots) ctx->local_slots = (uint32_t)v;
     }
     if (const char* k = getenv("RT_LOCAL_WINDOW")) {
         long v = atol(k);
         if (v >= 1 && v <= 256) ctx->local_window = floor_pow2((uint32_t)v);
-    }
-    if (const char* k = getenv("RT_LOCAL_STAGE")) {
-        long v = atol(k);
-        if (v >= 64 && v <= (1l << 22)) ctx->local_stage_paths = (uint32_t)v;
     }
     if (const char* k = getenv("RT_LOCAL_FLAT")) ctx->local_flat_allowed = atoi(k) != 0;
     if (const char* k = getenv("RT_WAVE_SLOTS")) {
@@ -1567,7 +1630,7 @@ int rt_sync(RtContext* ctx) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return RT_OK;
+    return check_render_error(ctx);
 }
 
 int rt_read_accum(RtContext* ctx, float* rgba_out) {
@@ -1579,7 +1642,7 @@ int rt_read_accum(RtContext* ctx, float* rgba_out) {
                                  (size_t)ctx->width * ctx->height * sizeof(float4),
                                  cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return RT_OK;
+    return check_render_error(ctx);
 }
 
 int rt_write_accum(RtContext* ctx, const float* rgba_in) {
@@ -1612,6 +1675,53 @@ int rt_tonemap_rgb8(RtContext* ctx, uint32_t sample_total, uint8_t* rgb8_out) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_rgb);
     if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "tone-map pass failed: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
+int rt_debug_view(RtContext* ctx, uint32_t dev_index, uint32_t environment_index, uint32_t sample_index,
+                  float* rgba_out) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!rgba_out) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "output pointer is NULL");
+    if (dev_index != 2u && dev_index != 3u)
+        return fail(ctx, RT_ERR_INVALID_ARGUMENT, "dev_index %u is not a view: only 2 (environment sampling "
+                    "distribution) and 3 (environment texels) leave the path tracer", dev_index);
+    if (!ctx->width || !ctx->height) return fail(ctx, RT_ERR_STATE, "no render target (rt_resize)");
+    if (environment_index >= ctx->envs.size())
+        return fail(ctx, RT_ERR_INVALID_ARGUMENT, "environment index %u out of range (%zu loaded)",
+                    environment_index, ctx->envs.size());
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const RtContext::Env& e = ctx->envs[environment_index];
+    EnvView env;
+    env.texture = e.texture;
+    env.alias = e.d_alias;
+    env.texels = e.d_texels;
+    env.width = e.width;
+    env.height = e.height;
+    const size_t count = (size_t)ctx->width * ctx->height;
+    float4* d_out = nullptr;
+    uint32_t* d_counts = nullptr;
+    RT_CUDA(ctx, cudaMalloc(&d_out, count * sizeof(float4)));
+    cudaError_t ce = cudaSuccess;
+    dim3 block(16, 16), grid((ctx->width + 15u) / 16u, (ctx->height + 15u) / 16u);  // the shader's workgroups
+    if (dev_index == 2u) {
+        ce = cudaMalloc(&d_counts, count * sizeof(uint32_t));
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(d_counts, 0, count * sizeof(uint32_t), ctx->stream);
+        if (ce == cudaSuccess) {
+            view_distribution_count_kernel<<<grid, block, 0, ctx->stream>>>(env, ctx->width, ctx->height, sample_index, d_counts);
+            view_distribution_resolve_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(d_counts, d_out, count);
+            ctx->launches += 2;
+            ce = cudaGetLastError();
+        }
+    } else {
+        view_environment_kernel<<<grid, block, 0, ctx->stream>>>(env, ctx->width, ctx->height, d_out);
+        ctx->launches++;
+        ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(rgba_out, d_out, count * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_out);
+    cudaFree(d_counts);
+    if (ce != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "debug view failed: %s", cudaGetErrorString(ce));
     return RT_OK;
 }
 

@@ -229,3 +229,78 @@ def test_memory_budget_does_not_change_the_image(rt, house, env_small):
     b.render_samples(24)
     assert b.read_accum().tobytes() == want.tobytes()
     assert b.memory_usage() < a.memory_usage()
+
+
+# ---------------------------------------------------------------- dev_index views, environment slots
+def _two_skies(rt):
+    a = rt.Environment.synthetic(64, 32)
+    rgb = np.ascontiguousarray(a.rgb[::-1, ::-1] * np.float32(0.5) + np.float32(0.125))  # a different sky
+    return rt.EnvironmentMaps([a, rt.Environment(rgb)])
+
+
+def test_debug_view_environment_texels(rt, house):
+    # dev_index 3 (shader.wgsl:1332-1338): saturate(environment texel at the pixel), f16 texture
+    envs = _two_skies(rt)
+    w, h = 96, 54
+    st = rt.State(house, envs, w, h, environment_index=1)
+    got = st.debug_view(3)
+    rgb = envs.environments[1].rgb
+    want = np.zeros((h, w, 4), dtype=np.float32)
+    want[:32, :64, :3] = np.clip(rgb, 0.0, 1.0).astype(np.float16).astype(np.float32)
+    assert got.tobytes() == want.tobytes()
+    with pytest.raises(rt.RtError):
+        st.debug_view(1)   # not a view: dev_index 1 renders normally in the reference
+
+
+def test_debug_view_sampling_distribution(rt, orc, house):
+    # dev_index 2 (shader.wgsl:1314-1331) against a numpy walk over the same alias table and RNG
+    import ctypes as C
+    envs = _two_skies(rt)
+    w, h, sample = 48, 27, 5
+    st = rt.State(house, envs, w, h)
+    got = st.debug_view(2, sample_index=sample)
+    env = envs.environments[0]
+    prob = env.alias[:, 0].view(np.float32)
+    alias = env.alias[:, 1]
+    length = env.width * env.height
+    lib = orc.lib()
+    counts = np.zeros((h, w), dtype=np.int64)
+    state = C.c_uint32()
+    for y in range(h):
+        for x in range(w):
+            lib.oracle_rng_seed(y * w + x, sample, C.byref(state))
+            for _ in range(20):
+                index = min(int(np.float32(lib.oracle_rng_uniform(C.byref(state))) * np.float32(length)), length - 1)
+                pick = index if lib.oracle_rng_uniform(C.byref(state)) < prob[index] else int(alias[index])
+                ex, ey = pick % env.width, pick // env.width
+                if ex < w and ey < h:
+                    counts[ey, ex] += 1
+    assert counts.sum() > 0
+    want = np.zeros((h, w, 4), dtype=np.float32)
+    step = np.float32(0.1) / np.float32(20.0)
+    for (y, x), k in np.ndenumerate(counts):
+        c = np.float32(0.0)
+        for _ in range(int(k)):
+            nxt = np.float32(np.float16(c + step))
+            if nxt == c:
+                break
+            c = nxt
+        want[y, x, :3] = c
+    assert got.tobytes() == want.tobytes()
+
+
+def test_environment_slot_cycling(rt, orc, house):
+    # the next_environment key (camera.rs:271-278): slot 0 -> 1 -> back to 0, accumulation restarts
+    envs = _two_skies(rt)
+    w, h = 128, 72
+    st = rt.State(house, envs, w, h, max_bounces=8)
+    images = []
+    for expect_slot in (0, 1, 0):
+        assert st.environment_index == expect_slot and st.sample_count == 0
+        st.render_samples(3)
+        got = st.read_accum()
+        want, _ = orc.Oracle(house, envs, w, h, max_bounces=8, environment_index=expect_slot).render(0, 3)
+        assert got.tobytes() == want.tobytes()
+        images.append(got)
+        st.next_environment()
+    assert images[0].tobytes() == images[2].tobytes() != images[1].tobytes()

@@ -205,3 +205,21 @@ def test_oracle_command_line(rt, orc, tmp_path):
     assert os.path.getsize(out["alias.bin"]) == 16 * 2048 * 1024
     report = json.load(open(out["c.json"]))
     assert report["render_counters"]["rays"] == counters["rays"] and report["counts"] == c
+
+
+def test_fan_anchor_report_is_current():
+    # wavefront_obj's fan anchoring is restated from memory (last corner). The committed report
+    # says what would move under the other reading (first corner): never the BVH topology or the
+    # primitive order, only which triangle of a split quad a ray lands in and last-bit distances.
+    import subprocess
+    import sys
+    from conftest import ROOT
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fan_anchor_report.py"), "--check"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, "tests/golden/fan_anchor_report.json is stale: rerun tools/fan_anchor_report.py"
+    with open(os.path.join(ROOT, "tests", "golden", "fan_anchor_report.json")) as fh:
+        rep = json.load(fh)
+    for name, s in rep["scenes"].items():
+        assert s["bvh_topology_identical"] and s["bvh_bounds_identical"] and s["primitive_order_identical"], name
+        assert s["first_hit_t_max_rel_diff"] < 1e-5 and s["image_rel_rmse"] < 0.01, name
