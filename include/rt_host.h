@@ -88,6 +88,11 @@ void rt_hdri_synthetic(uint32_t width, uint32_t height, float* rgb);
 /* AliasTable::build_by_luminance (environments.rs:97-186). out has width*height entries. */
 int rt_alias_build(uint32_t width, uint32_t height, const float* rgb, RtAliasEntry* out,
                    uint32_t* leftover_count);
+/* The same table by the literal single-threaded loop of environments.rs:123-178 (two stacks, a
+ * residual array, assigned flags): rt_alias_build is multi-threaded and stack-free and must equal
+ * this byte for byte. */
+int rt_alias_build_serial(uint32_t width, uint32_t height, const float* rgb, RtAliasEntry* out,
+                          uint32_t* leftover_count);
 /* Texture::from_rgb32float texel padding (texture.rs:104-118): rgba = (r,g,b,0). */
 void rt_rgb_to_rgba(uint32_t pixel_count, const float* rgb, float* rgba);
 

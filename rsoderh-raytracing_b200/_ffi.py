@@ -129,6 +129,7 @@ HOST_SIGNATURES = {
     "rt_hdr_write": (C.c_int, [C.c_char_p, _u32, _u32, _f3]),
     "rt_hdri_synthetic": (None, [_u32, _u32, _f3]),
     "rt_alias_build": (C.c_int, [_u32, _u32, _f3, _vp, C.POINTER(_u32)]),
+    "rt_alias_build_serial": (C.c_int, [_u32, _u32, _f3, _vp, C.POINTER(_u32)]),
     "rt_rgb_to_rgba": (None, [_u32, _f3, _f3]),
     "rt_png_write_rgb8": (C.c_int, [C.c_char_p, _u32, _u32, _vp]),
     "rt_pfm_write_rgb": (C.c_int, [C.c_char_p, _u32, _u32, _f3, _u32]),

@@ -3,7 +3,11 @@
 // table of src/environments.rs:87-186.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
 
 #include "scene.hpp"
 
@@ -171,7 +175,138 @@ void hdri_synthetic(uint32_t w, uint32_t h, float* rgb) {
     }
 }
 
+// Runs fn(t, begin, end) over [0, n) cut into one contiguous range per thread.
+template <typename F>
+static void parallel_ranges(size_t n, int threads, F fn) {
+    if (threads <= 1 || n < (size_t)1 << 14) {
+        fn(0, (size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) {
+        const size_t lo = n * (size_t)t / (size_t)threads, hi = n * (size_t)(t + 1) / (size_t)threads;
+        pool.emplace_back([=] { fn(t, lo, hi); });
+    }
+    for (auto& th : pool) th.join();
+}
+
+// AliasTable::build_by_luminance (environments.rs:97-186), byte-identical to the literal loop of
+// alias_build_serial below (tests/test_abi_and_env.py), organised for speed:
+//  * weights, normalisation and the small / large partition run on all host threads;
+//  * the f32 sum stays one sequential chain (environments.rs:110 — its rounding is the contract);
+//  * the pairing loop keeps no stacks. Both stacks start as ascending index lists and are popped
+//    from the end, and the only element ever pushed is the large entry just popped — onto the top
+//    of one of the two stacks, from where the next iteration takes it again. So a cursor into each
+//    list, the current large entry with its remaining weight in a register, and one carried
+//    "became small" entry reproduce the stack discipline exactly, with no per-entry residual array
+//    and no `assigned` flags: what was never assigned is what is left of the two lists.
 uint32_t alias_build(uint32_t w, uint32_t h, const float* rgb, RtAliasEntry* out) {
+    const size_t length = (size_t)w * h;
+    const float kPi = 3.14159274f;  // std::f32::consts::PI (environments.rs:1)
+    int threads = (int)std::thread::hardware_concurrency();
+    threads = threads < 1 ? 1 : (threads > 32 ? 32 : threads);
+    if (const char* k = std::getenv("RT_HOST_THREADS")) threads = std::atoi(k) > 0 ? std::atoi(k) : 1;
+
+    std::vector<float> row_sin(h);
+    for (uint32_t y = 0; y < h; y++) {
+        float angle = kPi * ((float)y + 0.5f) / (float)h;
+        row_sin[y] = (float)std::sin((double)angle);
+    }
+    std::unique_ptr<float[]> prob(new float[length]);  // first touched by the threads that fill it
+    parallel_ranges(h, threads, [&](int, size_t y0, size_t y1) {
+        for (size_t y = y0; y < y1; y++)
+            for (uint32_t x = 0; x < w; x++) {
+                const float* c = rgb + (y * w + x) * 3;
+                float lum = 0.2126f * c[0] + 0.7152f * c[1] + 0.0722f * c[2];  // environments.rs:88-90
+                prob[y * w + x] = lum * row_sin[y];
+            }
+    });
+    float weight_sum = 0.f;  // sequential f32 sum (environments.rs:110)
+    for (size_t i = 0; i < length; i++) weight_sum += prob[i];
+    const float length_f = (float)length;
+
+    // normalise; count the entries below / not below 1 per range, then write the two ascending lists
+    std::vector<size_t> n_small((size_t)threads + 1, 0), n_large((size_t)threads + 1, 0);
+    parallel_ranges(length, threads, [&](int t, size_t lo, size_t hi) {
+        size_t ns = 0;
+        for (size_t i = lo; i < hi; i++) {
+            prob[i] = prob[i] * length_f / weight_sum;
+            ns += prob[i] < 1.f ? 1u : 0u;
+            out[i].pmf = prob[i] / length_f;  // environments.rs:146 (entries never assigned get 1 / N below)
+            out[i]._pad = 0;
+        }
+        n_small[(size_t)t + 1] = ns;
+        n_large[(size_t)t + 1] = (hi - lo) - ns;
+    });
+    for (int t = 0; t < threads; t++) {
+        n_small[(size_t)t + 1] += n_small[(size_t)t];
+        n_large[(size_t)t + 1] += n_large[(size_t)t];
+    }
+    const size_t small_count = n_small[(size_t)threads], large_count = n_large[(size_t)threads];
+    std::unique_ptr<uint32_t[]> small(new uint32_t[small_count + 1]), large(new uint32_t[large_count + 1]);
+    parallel_ranges(length, threads, [&](int t, size_t lo, size_t hi) {
+        size_t ks = n_small[(size_t)t], kl = n_large[(size_t)t];
+        for (size_t i = lo; i < hi; i++) {
+            if (prob[i] < 1.f) small[ks++] = (uint32_t)i;
+            else large[kl++] = (uint32_t)i;
+        }
+    });
+
+    // environments.rs:134-159
+    size_t ks = small_count, kl = large_count;
+    const uint32_t kNoEntry = 0xFFFFFFFFu;
+    uint32_t carried = kNoEntry;  // a large entry that fell below 1: on top of the small stack
+    float carried_weight = 0.f;
+    uint32_t cur = kNoEntry;      // the large entry on top of the large stack, its weight in a register
+    float cur_weight = 0.f;
+    uint32_t stranded = kNoEntry;  // popped from the small stack when the large stack was empty
+    for (;;) {
+        uint32_t s;
+        float s_weight;
+        if (carried != kNoEntry) {
+            s = carried;
+            s_weight = carried_weight;
+            carried = kNoEntry;
+        } else {
+            if (ks == 0) break;
+            s = small[--ks];
+            s_weight = prob[s];
+        }
+        if (cur == kNoEntry) {
+            if (kl == 0) {
+                stranded = s;  // environments.rs:136-141: popped before the large stack is checked
+                break;
+            }
+            cur = large[--kl];
+            cur_weight = prob[cur];
+        }
+        out[s].probability = s_weight;
+        out[s].alias_index = cur;
+        cur_weight -= 1.f - s_weight;
+        if (cur_weight < 1.f) {
+            carried = cur;
+            carried_weight = cur_weight;
+            cur = kNoEntry;
+        }
+    }
+    // environments.rs:162-178: everything never assigned keeps itself
+    auto keep = [&](uint32_t i) {
+        out[i].probability = 1.f;
+        out[i].alias_index = i;
+        out[i].pmf = 1.f / length_f;
+        out[i]._pad = 0;
+    };
+    uint32_t leftover = 0;
+    for (size_t i = 0; i < ks; i++, leftover++) keep(small[i]);
+    for (size_t i = 0; i < kl; i++, leftover++) keep(large[i]);
+    if (cur != kNoEntry) keep(cur), leftover++;
+    if (stranded != kNoEntry) keep(stranded), leftover++;
+    return leftover;
+}
+
+// The literal statement of the same function (vectors as stacks, residual array, assigned flags):
+// what alias_build is checked against.
+uint32_t alias_build_serial(uint32_t w, uint32_t h, const float* rgb, RtAliasEntry* out) {
     const size_t length = (size_t)w * h;
     const float kPi = 3.14159274f;  // std::f32::consts::PI (environments.rs:1)
     // environments.rs:98-106: weight = luminance * sin(PI * (y + 0.5) / height).

@@ -268,6 +268,14 @@ int rt_alias_build(uint32_t width, uint32_t height, const float* rgb, RtAliasEnt
     return RT_OK;
 }
 
+int rt_alias_build_serial(uint32_t width, uint32_t height, const float* rgb, RtAliasEntry* out,
+                          uint32_t* leftover_count) {
+    if (!rgb || !out || !width || !height) return RT_ERR_INVALID_ARGUMENT;
+    uint32_t leftover = rt::alias_build_serial(width, height, rgb, out);
+    if (leftover_count) *leftover_count = leftover;
+    return RT_OK;
+}
+
 void rt_rgb_to_rgba(uint32_t pixel_count, const float* rgb, float* rgba) {
     for (uint32_t i = 0; i < pixel_count; i++) {
         rgba[4 * (size_t)i + 0] = rgb[3 * (size_t)i + 0];

@@ -121,6 +121,7 @@ void hdr_decode(const uint8_t* bytes, size_t len, uint32_t* w, uint32_t* h, std:
 std::vector<uint8_t> hdr_encode_flat(uint32_t w, uint32_t h, const float* rgb);
 void hdri_synthetic(uint32_t w, uint32_t h, float* rgb);
 uint32_t alias_build(uint32_t w, uint32_t h, const float* rgb, RtAliasEntry* out);
+uint32_t alias_build_serial(uint32_t w, uint32_t h, const float* rgb, RtAliasEntry* out);  // literal form
 
 // Config D generator.
 void build_synthetic_field(const std::string& assets_dir, uint32_t grid, uint32_t seed,

@@ -164,6 +164,38 @@ def test_alias_table_bit_exact_vs_numpy_restatement(rt, scene_oracle, w, h):
     assert env.leftover_count == leftover
 
 
+def _alias(rt, fn, rgb):
+    import ctypes as C
+    rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+    h, w, _ = rgb.shape
+    table = np.zeros((w * h, 4), dtype=np.uint32)
+    leftover = C.c_uint32()
+    st = fn(w, h, rgb.ctypes.data_as(C.POINTER(C.c_float)), table.ctypes.data_as(C.c_void_p), C.byref(leftover))
+    assert st == 0
+    return table, leftover.value
+
+
+@pytest.mark.parametrize("case", ["sky2k", "random", "uniform", "tiny", "one_bright", "heavy_tail", "all_black_but_one"])
+def test_threaded_stack_free_alias_build_equals_the_literal_loop(rt, env_2k, case, monkeypatch):
+    # rt_alias_build (all host threads, cursors instead of stacks) vs rt_alias_build_serial (the
+    # literal environments.rs:97-186 loop), byte for byte, also with other thread counts.
+    rng = np.random.default_rng(7)
+    rgb = {"sky2k": lambda: env_2k.environments[0].rgb,
+           "random": lambda: rng.random((300, 517, 3), dtype=np.float32) ** 8 * 50,
+           "uniform": lambda: np.full((64, 128, 3), 0.5, dtype=np.float32),
+           "tiny": lambda: rng.random((3, 5, 3), dtype=np.float32),
+           "one_bright": lambda: np.where(np.arange(64 * 32 * 3).reshape(32, 64, 3) // 3 == 777, 1000.0, 0.01),
+           "heavy_tail": lambda: rng.random((512, 1024, 3), dtype=np.float32) ** 20 * 1e4,
+           "all_black_but_one": lambda: np.where(np.arange(16 * 8 * 3).reshape(8, 16, 3) // 3 == 5, 3.0, 0.0)}[case]()
+    lib = rt._ffi.host_lib()
+    want, want_left = _alias(rt, lib.rt_alias_build_serial, rgb)
+    for threads in ("", "1", "3"):
+        if threads:
+            monkeypatch.setenv("RT_HOST_THREADS", threads)
+        got, got_left = _alias(rt, lib.rt_alias_build, rgb)
+        assert got.tobytes() == want.tobytes() and got_left == want_left, f"threads={threads or 'all'}"
+
+
 def test_alias_table_properties_full_size(env_2k):
     env = env_2k.environments[0]
     n = env.width * env.height
