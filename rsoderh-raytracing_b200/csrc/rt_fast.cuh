@@ -1,5 +1,9 @@
-// rt_fast.cuh — the production render path: persistent thread-per-pixel path tracing
-// over a two-children-per-fetch BVH layout, for sm_100a.
+// rt_fast.cuh — the traversal and shading building blocks every render kernel shares (two-children-
+// per-fetch BVH records, the hoisted analytic pre-pass, the tie rule, the flat leaf-mask walk, hit
+// reconstruction, shade_hit), plus two kernels that are NOT the render path: `render_fast_kernel`
+// (RT_KERNEL=fast), a thread-per-pixel megakernel over the same code kept as a cross-check of the
+// wavefront kernels, and `first_hit_fast_kernel`, the primary-ray parity hook behind rt_first_hit.
+// The render path is rt_local.cuh (per-warp wavefront engines) / rt_wave.cuh (one launch per stage).
 //
 // Semantics follow /root/reference/src/shaders/shader.wgsl (cast_ray_bvh 469-564,
 // cast_ray 567-601, trace_ray 1213-1303, main 1305-1373); the arithmetic is
@@ -22,9 +26,6 @@
 //  * Ties (equal distance, bit for bit) are resolved as the reference's strict `<` in
 //    visiting order does: lower slot first inside a leaf; across leaves by the sign of
 //    1/d on the split axis of the lowest common ancestor (`precedes`).
-//  * One thread owns one pixel for all its samples and issues ONE ray per loop
-//    iteration — the next closest-hit ray or a pending shadow ray — so the traversal
-//    code exists once and every lane of a warp enters it on every iteration.
 #pragma once
 
 #include "rt_device.cuh"

@@ -179,6 +179,38 @@ def test_sky_only_scene_matches_closed_form(rt, orc, env_small):
         assert np.allclose(acc[y, x, :3], want, rtol=1e-6, atol=1e-7), (x, y, acc[y, x], want)
 
 
+def test_white_furnace_energy(rt, orc):
+    # A constant environment of radiance c around one big sphere. Background pixels have a closed
+    # form: c / (1 + pdf^2) with the uniform-sphere pdf 1 / (4 pi') that the luminance x sin(theta)
+    # alias table yields for a constant map (pi' = the shader's 3.14159). Pixels on the sphere
+    # estimate the hemispherical albedo of the Lambert + GGX BSDF times c: with MIS and next-event
+    # estimation in place they must not gain energy (<= c within noise), and a white rough
+    # dielectric keeps most of it. A wrong MIS weight, pdf or cosine shows up here at once.
+    c = np.float32(0.75)
+    sky = rt.Environment(np.full((32, 64, 3), c, dtype=np.float32))
+    envs = rt.EnvironmentMaps([sky])
+    scene = (rt.SceneBuilder().add_material((1, 1, 1), 1, 0).add_sphere((0, 0, -3), 1.0, 0)
+             .set_camera((0, 0, 0), 0, 0, math.radians(60)).build())
+    w, h, spp = 64, 36, 96
+    ora = orc.Oracle(scene, envs, w, h, max_bounces=10)
+    acc, counters = ora.render(0, spp)
+    img = acc[..., :3] / np.float32(spp)
+    slots, _, _ = ora.first_hit(0)
+    on_sphere = slots != MISS
+    assert 0.1 < on_sphere.mean() < 0.6
+    pdf = 1.0 / (4.0 * 3.14159)
+    assert np.allclose(img[0, 0], c / (1.0 + pdf * pdf), rtol=2e-3)     # corner pixel: always background
+    # the jittered camera rays of edge pixels mix both, so look at the disc's interior only
+    ys, xs = np.nonzero(on_sphere)
+    cy, cx = ys.mean(), xs.mean()
+    r = np.sqrt(on_sphere.sum() / np.pi)
+    inner = on_sphere & (((np.arange(h)[:, None] - cy) ** 2 + (np.arange(w)[None, :] - cx) ** 2) < (0.8 * r) ** 2)
+    mean = float(img[inner].mean())
+    assert 0.80 * c < mean <= 1.005 * c, mean
+    assert float(img[inner].max()) < 1.25 * c      # no fireflies above the furnace level
+    assert counters["shadow_rays"] > 0 and counters["env_lookups"] > 0
+
+
 def test_oracle_command_line(rt, orc, tmp_path):
     # oracle/cli.py writes what the parity checks compare; its outputs equal the API's
     import json
