@@ -1,14 +1,15 @@
 // rt_backend.cu — kernels and extern "C" surface of librt_backend.so (include/rt_backend.h).
 //
 // Replaces the reference's device/pipeline layer (src/state.rs) and its compute shader
-// (src/shaders/shader.wgsl) with sm_100a CUDA. The render path is the persistent CTA-local
-// wavefront kernel of rt_local.cuh (one asynchronous launch per rt_render). This file holds
-// the C ABI, the uploads, and two cross-check kernels that are NOT the product path:
+// (src/shaders/shader.wgsl) with sm_100a CUDA. The render path is the wavefront pipeline of
+// rt_wave.cuh (four dense kernels per wave on two streams). This file holds the C ABI, the
+// uploads, and the kernels that are NOT the product path but cross-checks of it:
 // `render_kernel` / `first_hit_kernel` below walk the reference-layout arrays in the
 // reference's order, one thread per pixel, and count node / primitive tests exactly like the
-// CPU restatement the tests compare with (rt_set_detailed_counters; RT_KERNEL=pixel) — the source of the algorithmic work
-// figures bench.py reports. RT_KERNEL=wave / fast select the superseded pipelines of
-// rt_wave.cuh / rt_fast.cuh, kept so the tests can check that every kernel agrees bit for bit.
+// CPU restatement the tests compare with (rt_set_detailed_counters; RT_KERNEL=pixel) — the
+// source of the algorithmic work figures bench.py reports. RT_KERNEL=local selects the
+// persistent single-launch kernel of rt_local.cuh, RT_KERNEL=fast the thread-per-pixel
+// megakernel of rt_fast.cuh; the tests check that all four agree bit for bit.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -459,9 +460,9 @@ struct RtContext {
     // persistent CTA-local wavefront (rt_local.cuh)
     void* local_arena = nullptr;
     size_t local_arena_bytes = 0;
-    uint32_t local_slots = 128;           // path slots per warp
-    uint32_t local_window = 4;            // samples per window (power of two)
-    uint32_t* local_error_word = nullptr; // device word a stalled warp sets (rt_local.cuh)
+    uint32_t local_slots = 1024;          // path slots per CTA
+    uint32_t local_window = 16;           // samples per window (power of two)
+    uint32_t local_stage_paths = 8192;    // parked samples per CTA (ring of windows)
     bool local_flat_allowed = false;      // measured: the stack walk is faster (profiles/README.md, r2)
     size_t local_smem_set[2] = {0, 0};    // dynamic shared memory opted in per kernel form
     unsigned long long* d_local_profile = nullptr;  // 11 x u64 (LocalParams::profile)
@@ -895,46 +896,38 @@ int local_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin,
     p.counters = ctx->d_counters;
     p.width = ctx->width;
     p.height = ctx->height;
+    p.tiles_x = (ctx->width + 7u) / 8u;
+    p.tiles_total = p.tiles_x * ((ctx->height + 7u) / 8u);
     p.sample_begin = sample_begin;
     p.sample_count = sample_count;
     p.max_bounces = max_bounces;
-
-    const uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)rtl::kMinBlocks;
-    const uint32_t warps = grid * (uint32_t)rtl::kWarps;
-    // Tiles are the unit of load balance: 8x4 pixels, 4x4 when the frame has few of them.
-    p.tile_w_shift = 3u;
-    p.tile_shift = 5u;
-    if ((uint64_t)((ctx->width + 7u) / 8u) * ((ctx->height + 3u) / 4u) < 4ull * warps) {
-        p.tile_w_shift = 2u;
-        p.tile_shift = 4u;
-    }
-    const uint32_t tile_w = 1u << p.tile_w_shift, tile_h = (1u << p.tile_shift) >> p.tile_w_shift;
-    p.tiles_x = (ctx->width + tile_w - 1u) / tile_w;
-    p.tiles_total = p.tiles_x * ((ctx->height + tile_h - 1u) / tile_h);
 
     const bool flat = ctx->local_flat_allowed && ctx->fast.flat_leaves > 0u;
     const uint32_t window = floor_pow2(sample_count < ctx->local_window ? sample_count : ctx->local_window);
     uint32_t shift = 0;
     while ((1u << shift) < window) shift++;
     p.window_shift = shift;
-    p.ring_entries = rtl::kRing;
-    p.slots = ctx->local_slots;
-    p.qcap = 32u;
-    while (p.qcap < p.slots) p.qcap *= 2u;
+    uint32_t ring = floor_pow2(ctx->local_stage_paths / (64u * window) > 0u ? ctx->local_stage_paths / (64u * window) : 1u);
+    if (ring > rtl::kRing) ring = rtl::kRing;
+    p.ring_entries = ring;
     // few samples per tile: take several tiles per atomic so that one grab feeds the slots once
-    const uint64_t per_tile = (uint64_t)(1u << p.tile_shift) * sample_count;
-    uint32_t grab = (uint32_t)((p.slots + per_tile - 1) / per_tile);
+    const uint64_t per_tile = 64ull * sample_count;
+    uint32_t grab = (uint32_t)((ctx->local_slots + per_tile - 1) / per_tile);
     p.tile_grab = grab < 1u ? 1u : (grab > 64u ? 64u : grab);
 
-    const size_t T = (size_t)warps * p.slots;
-    const size_t stage_f4 = (size_t)warps * (((size_t)p.ring_entries << shift) << p.tile_shift);
-    // rOD 32 + pTLPI 64 + sray_d 16 + hit 16 + fb 8 + occl 1 per slot, staging, tile counter + error word
+    // no more CTAs than tiles, no more slots than a CTA's share of the paths needs
+    const uint32_t grid_full = (uint32_t)ctx->sm_count * (uint32_t)rtl::kMinBlocks;
+    const uint32_t grid = p.tiles_total < grid_full ? p.tiles_total : grid_full;
+    p.slots = ctx->local_slots;
+
+    const size_t T = (size_t)grid_full * p.slots;
+    const size_t stage_f4 = (size_t)grid_full * ((size_t)ring * window * 64u);
+    // rOD 32 + pTLPI 64 + sray_d 16 + hit 16 + fb 8 + occl 1 per slot, staging, tile counter
     const size_t bytes = T * (32 + 64 + 16 + 16 + 8 + 1) + 256 + stage_f4 * sizeof(float4) + 256;
     if (!ctx->local_arena || ctx->local_arena_bytes < bytes) {
         RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->local_arena);
         ctx->local_arena = nullptr;
-        ctx->local_error_word = nullptr;
         ctx->local_arena_bytes = 0;
         RT_CUDA(ctx, cudaMalloc(&ctx->local_arena, bytes));
         ctx->local_arena_bytes = bytes;
@@ -947,12 +940,10 @@ int local_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin,
         p.hit = (float4*)q;     q += T * 16;
         p.staging = (float4*)q; q += stage_f4 * sizeof(float4);
         p.fb = (float2*)q;      q += T * 8;
-        p.next_tile = (uint32_t*)q;
-        p.error = (uint32_t*)q + 1; q += 256;
+        p.next_tile = (uint32_t*)q; q += 256;
         p.occl = (uint8_t*)q;
     }
-    ctx->local_error_word = p.error;
-    const size_t smem = rtl::smem_layout(p.scene, p.slots, p.qcap, flat).bytes;
+    const size_t smem = rtl::smem_layout(p.scene, p.slots, flat).bytes;
     if (ctx->local_smem_set[flat ? 1 : 0] < smem) {
         cudaError_t ce = flat ? cudaFuncSetAttribute(rtl::local_wave_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                               : cudaFuncSetAttribute(rtl::local_wave_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -960,13 +951,12 @@ int local_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin,
             return fail(ctx, RT_ERR_CUDA, "%zu bytes of shared memory per CTA refused: %s", smem, cudaGetErrorString(ce));
         ctx->local_smem_set[flat ? 1 : 0] = smem;
     }
-    RT_CUDA(ctx, cudaMemsetAsync(p.next_tile, 0, 2 * sizeof(uint32_t), ctx->stream));
+    RT_CUDA(ctx, cudaMemsetAsync(p.next_tile, 0, sizeof(uint32_t), ctx->stream));
     static const bool timeline_print = getenv("RT_LOCAL_PROFILE") != nullptr;
     const bool profiling = ctx->profiling || timeline_print;
-    constexpr int kProfileWords = 14;
     if (profiling) {
-        if (!ctx->d_local_profile) RT_CUDA(ctx, cudaMalloc(&ctx->d_local_profile, kProfileWords * sizeof(unsigned long long)));
-        RT_CUDA(ctx, cudaMemsetAsync(ctx->d_local_profile, 0, kProfileWords * sizeof(unsigned long long), ctx->stream));
+        if (!ctx->d_local_profile) RT_CUDA(ctx, cudaMalloc(&ctx->d_local_profile, 11 * sizeof(unsigned long long)));
+        RT_CUDA(ctx, cudaMemsetAsync(ctx->d_local_profile, 0, 11 * sizeof(unsigned long long), ctx->stream));
         p.profile = ctx->d_local_profile;
         RT_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
     }
@@ -976,9 +966,9 @@ int local_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin,
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "render kernel launch failed: %s", cudaGetErrorString(ce));
     if (profiling) {
-        // Stage shares of the one launch (clock64 per warp, lane 0, around every batch) scaled to its
+        // Phase shares of the one launch (clock64 per CTA, thread 0, at the barriers) scaled to its
         // CUDA-event duration. Profiling makes the call synchronous.
-        unsigned long long h[kProfileWords];
+        unsigned long long h[11];
         float ms = 0.f;
         RT_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
         RT_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_local_profile, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
@@ -988,23 +978,25 @@ int local_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin,
         double cyc = 0;
         for (int i = 0; i < 5; i++) cyc += (double)h[i];
         if (cyc <= 0) cyc = 1;
+        const double ctas = h[10] ? (double)h[10] : 1.0;
         // kernel order of RtWaveProfile: shade, finish, pre-pass, walk; bookkeeping goes to gap_ms
+        const int order[4] = {0, 2, 3, 4};
         ctx->profile.renders++;
+        ctx->profile.waves += (uint64_t)((double)h[9] / ctas + 0.5);
         for (int j = 0; j < 4; j++) {
             ctx->profile.launches[j] += 1;
-            ctx->profile.kernel_ms[j] += ms * (double)h[j] / cyc;
+            ctx->profile.kernel_ms[j] += ms * (double)h[order[j]] / cyc;
         }
-        ctx->profile.gap_ms += ms * (double)h[4] / cyc;
+        ctx->profile.gap_ms += ms * (double)h[1] / cyc;
         ctx->profile.total_ms += ms;
         if (timeline_print) {
-            auto per = [&](int j) { return h[9 + j] ? (double)h[5 + j] / (double)h[9 + j] : 0.0; };
-            fprintf(stderr, "[local profile] %s walk, %u warps x %u slots, tile %ux%u, window %u x ring %u: %.3f ms | shade %.1f%% "
-                    "finish %.1f%% prepass %.1f%% walk %.1f%% book %.1f%% | items per batch: shade %.1f finish %.1f "
-                    "prepass %.1f walk %.1f | batches per warp: %.0f %.0f %.0f %.0f\n",
-                    flat ? "flat" : "stack", warps, p.slots, tile_w, tile_h, window, p.ring_entries, ms,
+            const double w = h[9] ? (double)h[9] : 1.0;
+            fprintf(stderr, "[local profile] %s walk, %u CTAs x %u slots, window %u x ring %u: %.3f ms, %.0f waves per CTA, "
+                    "%.1f us per wave | shade %.1f%% book %.1f%% finish %.1f%% prepass %.1f%% walk %.1f%% | items per wave: "
+                    "shade %.0f finish %.0f rays %.0f walk %.0f\n",
+                    flat ? "flat" : "stack", grid, p.slots, window, ring, ms, (double)h[9] / ctas, ms * 1e3 / ((double)h[9] / ctas),
                     100.0 * h[0] / cyc, 100.0 * h[1] / cyc, 100.0 * h[2] / cyc, 100.0 * h[3] / cyc, 100.0 * h[4] / cyc,
-                    per(0), per(1), per(2), per(3), (double)h[9] / warps, (double)h[10] / warps, (double)h[11] / warps,
-                    (double)h[12] / warps);
+                    h[5] / w, h[6] / w, h[7] / w, h[8] / w);
         }
     }
     return RT_OK;
@@ -1030,18 +1022,6 @@ cudaError_t launch_first_hit(const FirstHitParams& p, uint32_t depth, cudaStream
     else if (depth <= 32) first_hit_kernel<COUNT, 32><<<grid, block, 0, stream>>>(p);
     else first_hit_kernel<COUNT, 64><<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
-}
-
-// After a stream synchronisation: did a warp of the persistent render kernel give up (its
-// scheduler found no work although paths were outstanding)? Never seen; it turns a would-be hang
-// into an error.
-int check_render_error(RtContext* ctx) {
-    if (!ctx->local_error_word) return RT_OK;
-    uint32_t flag = 0;
-    RT_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->local_error_word, sizeof flag, cudaMemcpyDeviceToHost, ctx->stream));
-    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (flag) return fail(ctx, RT_ERR_CUDA, "the render kernel stalled with paths outstanding (internal error)");
-    return RT_OK;
 }
 
 int check_ready(RtContext* ctx, uint32_t env_index, bool need_env) {
@@ -1110,11 +1090,15 @@ int rt_create(int device, RtContext** out) {
     }
     if (const char* k = getenv("RT_LOCAL_SLOTS")) {
         long v = atol(k);
-        if (v >= 32 && v <= (long)rtl::kMaxSlots) ctx->local_slots = (uint32_t)v;
+        if (v >= 64 && v <= (long)rtl::kMaxSlots) ctx->local_slots = (uint32_t)v;
     }
     if (const char* k = getenv("RT_LOCAL_WINDOW")) {
         long v = atol(k);
         if (v >= 1 && v <= 256) ctx->local_window = floor_pow2((uint32_t)v);
+    }
+    if (const char* k = getenv("RT_LOCAL_STAGE")) {
+        long v = atol(k);
+        if (v >= 64 && v <= (1l << 22)) ctx->local_stage_paths = (uint32_t)v;
     }
     if (const char* k = getenv("RT_LOCAL_FLAT")) ctx->local_flat_allowed = atoi(k) != 0;
     if (const char* k = getenv("RT_WAVE_SLOTS")) {
@@ -1630,7 +1614,7 @@ int rt_sync(RtContext* ctx) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return check_render_error(ctx);
+    return RT_OK;
 }
 
 int rt_read_accum(RtContext* ctx, float* rgba_out) {
@@ -1642,7 +1626,7 @@ int rt_read_accum(RtContext* ctx, float* rgba_out) {
                                  (size_t)ctx->width * ctx->height * sizeof(float4),
                                  cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return check_render_error(ctx);
+    return RT_OK;
 }
 
 int rt_write_accum(RtContext* ctx, const float* rgba_in) {

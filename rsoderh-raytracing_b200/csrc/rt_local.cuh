@@ -1,47 +1,55 @@
-// rt_local.cuh — the persistent render kernel: ONE launch per rt_render in which every WARP is
-// an independent little wavefront engine over its own pool of path slots.
+// rt_local.cuh — the persistent alternative to the launch-per-stage pipeline of rt_wave.cuh
+// (RT_KERNEL=local): ONE kernel per rt_render in which every CTA runs its own small wavefront
+// pipeline over a private pool of path slots. It is bit-exact with every other kernel, fully
+// asynchronous and needs 80 MB instead of gigabytes, but it is NOT the default: it renders
+// house.toml at 6.5-6.8 Grays/s against 7.85 for rt_wave.cuh. ncu says why (profiles/README.md,
+// round 2): the kernel is 112 KB of SASS, more than an SM's instruction cache holds while its
+// two CTAs sit in different phases, so it re-fetches phase code from the GPC-level instruction
+// cache all the time (sm__icc hit rate 94.8 %, gcc instruction requests at 71 % of their peak),
+// and 28 % of its stall samples wait at the phase barriers. Letting every WARP run the phases on
+// its own (experiments/rt_local_warp_engines.cuh: no barriers, full 32-lane batches) makes it
+// worse, not better: 32 warps in four code regions drop the hit rate to 54 %, saturate the
+// GPC instruction cache (98 % of peak, 66 % of stall samples "no instruction") and halve the
+// throughput. One launch per stage keeps each kernel's code (18-43 KB) resident: 99.8 % hits.
 //
-// The path loop of shader.wgsl:1213-1303 is cut at its ray casts into four stages, as in
-// rt_wave.cuh, but a stage is a batch of (up to) 32 queued items that one warp works on with
-// all its lanes, the queues between the stages live in the warp's own shared memory, and
-// nothing ever waits for another warp: no kernel boundaries, no __syncthreads, no atomics on
-// shared counters (a queue's head and tail are warp-uniform values).
+// The path loop of shader.wgsl:1213-1303 is cut at its ray casts into four phases, as in
+// rt_wave.cuh, but the phases are loops inside one kernel, separated by __syncthreads()
+// instead of kernel boundaries, and every CTA owns everything it touches:
 //
-//   shade    slots whose rays are all back and whose closest ray hit -> settle the last shadow
-//            ray, shade (emission, next-event set-up, BSDF sample), emit the bounce ray and the
-//            shadow ray into the ray queue
-//   finish   slots whose ray escaped / whose path ended, and idle slots -> sky light, park the
-//            finished sample in its window's staging block, take the next path of the warp's
-//            open windows (camera ray) and run that ray's pre-pass on the spot
-//   prepass  ray queue -> analytic pre-pass; rays with no triangle to test are settled here,
-//            the others go to the walk queue
-//   walk     walk queue -> triangle tests with persistent lanes: a lane takes the next ray
-//            the moment its own is finished. When the queue has run dry and only a few lanes
-//            are still walking, they are SUSPENDED (8 words per lane in shared memory; the
-//            traversal stack stays where it is) and resumed by the next walk batch, so the
-//            tail of a batch is not walked with a nearly empty warp.
+//   shade    slots whose ray hit -> settle the last shadow ray, shade (emission, next-event
+//            set-up, BSDF sample), emit the bounce ray + shadow ray into the CTA's ray queue
+//   finish   slots whose ray escaped / path ended / that hold no path -> sky light, park the
+//            finished sample, take the next path of the CTA's open windows (camera ray) and
+//            run that ray's pre-pass on the spot
+//   prepass  ray queue -> analytic pre-pass (+ the leaf-box mask of the flat walk); rays with
+//            no triangle to test are finished here, the others go to the walk queue
+//   walk     walk queue -> triangle tests; persistent lanes that take the next ray the
+//            moment their own is finished
 //
-// The scheduler of a warp runs whichever stage has a full batch waiting (walk, pre-pass,
-// shade, finish in that order), else the fullest one. A slot's rays are counted in a per-slot
-// word (`pend`); the lane that settles the last of them files the slot under shade or finish.
-//
-// What this buys over one kernel launch per stage (rt_wave.cuh):
-//   * no launches, no grid-wide or CTA-wide barriers: nothing to amortise, so the GPU holds
-//     ~600 K path slots instead of 8 Mi, and their state (137 B per slot) stays in L2 instead
-//     of streaming through DRAM four times per wave;
-//   * stage batches are full (32 of 32 lanes) whenever 32 items are queued, whatever the mix of
-//     path lengths;
+// What this buys over one kernel launch per phase (rt_wave.cuh):
+//   * no launches and no grid-wide barriers between phases: nothing to amortise, so a CTA's
+//     pool is ~1 K slots instead of 8 Mi for the whole GPU — 296 pools x 137 B x 1 K slots =
+//     41 MB of path state that stays in L2 (and partly in the SM's own L1, which a persistent
+//     kernel never flushes) instead of streaming 1.3 GB through DRAM four times per wave;
+//   * queues, lists and counters live in shared memory (atomics cost a few cycles);
 //   * rt_render is a single asynchronous launch; the pipeline is full from the first
 //     microsecond and drains one tile at a time, which is what a 32-spp share of a
 //     sample-split frame needs.
 //
-// Work distribution: the image is cut into small tiles (8x4 or 4x4 pixels) handed out from a
-// global counter. A warp renders ALL samples of a tile, in windows of W consecutive samples; a
-// window's tile_pixels x W paths are the work items its slots draw from. A finished sample is
-// parked in the window's staging block, and when the window's last path is in, the warp adds
-// its planes to the accumulation buffer in sample order — the reference's frame-by-frame
-// accumulation (shader.wgsl:1367-1371). Windows are committed in the order they were opened,
-// so every bit of the image is independent of scheduling.
+// Work distribution: the image is cut into 8x8-pixel tiles handed out from a global counter.
+// A CTA renders ALL samples of a tile, in windows of W consecutive samples; a window's
+// 64 x W paths are the work items its slots draw from. A finished sample is parked in the
+// window's staging block, and when the window's last path is in, 64 threads add its planes
+// to the accumulation buffer in sample order — the reference's frame-by-frame accumulation
+// (shader.wgsl:1367-1371). Windows are committed in the order they were opened, so every bit
+// of the image is independent of scheduling. Several windows (of one or more tiles) are open
+// at a time, so the slots never wait for a straggler path.
+//
+// The walk phase has two forms: for a scene whose effective tree has at most 32 leaves
+// (FastScene::flat — house.toml, default.toml) the pre-pass tests every leaf box in
+// straight-line code from shared memory and hands the walk a bit mask of the leaves to test,
+// in the ray's own visiting order; the walk then tests ONE triangle per lane and iteration,
+// with no stack and no node phase. Larger trees use the N2 stack walk of rt_fast.cuh.
 #pragma once
 
 #include "rt_fast.cuh"
@@ -56,24 +64,15 @@ using namespace rtf;
 #ifndef RT_LOCAL_MIN_BLOCKS
 #define RT_LOCAL_MIN_BLOCKS 2
 #endif
-#ifndef RT_LOCAL_MIN_BUSY
-#define RT_LOCAL_MIN_BUSY 16   // a walk batch whose queue is empty suspends below this many walking lanes
-#endif
 constexpr int kThreads = RT_LOCAL_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMinBlocks = RT_LOCAL_MIN_BLOCKS;
-constexpr uint32_t kMinBusy = RT_LOCAL_MIN_BUSY;
-constexpr uint32_t kRing = 8;          // windows in flight per warp, at most
+constexpr uint32_t kRing = 32;         // windows in flight per CTA, at most
 constexpr uint32_t kMaxCommit = 4;     // windows committed per maintenance step
-constexpr uint32_t kMaxSlots = 256;    // per warp
+constexpr uint32_t kFresh = 0x8000u;   // finish-list entry: the slot holds no path
 constexpr uint32_t kShadow = 0x8000u;  // ray / walk queue entry: the slot's shadow ray
 constexpr uint32_t kSlotMask = 0x7FFFu;
-constexpr uint32_t kFull = 0xFFFFFFFFu;
-// per-slot `pend` word: rays not settled yet | the closest-hit ray found something | the path is over
-constexpr uint32_t kPendCount = 0xFFu, kPendHit = 0x100u, kPendDone = 0x200u;
-constexpr uint32_t kStallLimit = 100000u;  // scheduler rounds without work before the warp gives up
-
-enum Queue : uint32_t { Q_SHADE = 0, Q_FIN, Q_FREE, Q_RAY, Q_WALK, Q_COUNT };
+constexpr uint32_t kMaxSlots = 0x7FFFu;
 
 // low byte of the path record's last word; the other bytes hold the ring entry and the
 // pixel's position inside its tile
@@ -84,26 +83,26 @@ enum PathState : uint32_t {
 constexpr uint32_t kFlagShadow = 1u;  // a shadow ray was cast for the last shaded hit
 
 struct RingEntry {
-    uint32_t tx, ty;     // tile
+    uint32_t tx, ty;     // tile (8x8 pixels)
     uint32_t w0, count;  // first sample of the window, samples in it
     uint32_t left;       // paths of the window that have not parked their sample yet
     uint32_t pad[3];
 };
 
-struct WarpCtrl {
-    uint32_t head[Q_COUNT], tail[Q_COUNT];  // running indices; entry i sits at i & (capacity - 1)
+struct LocalCtrl {
+    uint32_t n_shade[2], n_fin[2];   // list lengths, by wave parity
+    uint32_t n_ray, n_walk, walk_head;
     uint32_t handed, limit;          // path handout: virtual indices < limit belong to open windows
     uint32_t ring_head, ring_tail;   // windows [head, tail) are open or waiting for their commit
     uint32_t tile_next, tile_end;    // tiles taken from the global counter, not yet opened
     uint32_t tile_valid, cur_tx, cur_ty, next_window;
     uint32_t exhausted;              // the global counter has run out
-    uint32_t n_susp;                 // lanes holding a suspended walk
     uint32_t commit_n;
-    uint32_t pad0;
+    uint32_t quit;
+    // profiling (LocalParams::profile): cycles per phase, items per phase, waves
+    unsigned long long t_last, cycles[5], items[4], waves;
     RingEntry commit[kMaxCommit];
     RingEntry ring[kRing];
-    // profiling (LocalParams::profile): cycles per stage (+ bookkeeping), items and batches per stage
-    unsigned long long cycles[5], items[4], batches[4];
 };
 
 struct LocalParams {
@@ -114,15 +113,13 @@ struct LocalParams {
     unsigned long long* counters;
     uint32_t width, height;
     uint32_t tiles_x, tiles_total;
-    uint32_t tile_w_shift, tile_shift;  // tile = (1 << tile_w_shift) x (tile pixels >> tile_w_shift); pixels = 1 << tile_shift
     uint32_t sample_begin, sample_count;
     uint32_t max_bounces;
-    uint32_t slots;          // path slots per warp (<= kMaxSlots)
-    uint32_t qcap;           // queue capacity: power of two >= slots
+    uint32_t slots;          // path slots per CTA (<= kMaxSlots)
     uint32_t window_shift;   // W = 1 << window_shift samples per window
     uint32_t ring_entries;   // power of two <= kRing
     uint32_t tile_grab;      // tiles taken per atomic on the global counter
-    // per-warp pools, indexed by global warp * slots + slot
+    // per-CTA pools, indexed by blockIdx.x * slots + slot
     float4* rOD;      // [2] ray origin (.w = closest analytic distance), direction (.w = bits rec of it)
     float4* pTLPI;    // [4] throughput + last_pdf, radiance + bits rng, pending light + bits flags,
                       //     bits (pixel, sample, bounce, state | ring entry << 8 | pixel in tile << 16)
@@ -130,34 +127,27 @@ struct LocalParams {
     float4* hit;      // (t, bits rec, u, v)
     float2* fb;       // brute-force fallback winner of the closest-hit ray
     uint8_t* occl;    // 1 when the shadow ray is blocked
-    float4* staging;  // [warp][ring_entries][W][tile pixels] parked samples
+    float4* staging;  // [CTA][ring_entries][W][64] parked samples
     uint32_t* next_tile;
-    uint32_t* error;  // set when a warp's scheduler found no work although paths were outstanding
-    // optional: [0..4] cycles in shade, finish, pre-pass, walk, bookkeeping summed over warps, [5..8]
-    // items those stages worked on, [9..12] their batches, [13] warps
+    // optional: [0..4] cycles in shade, window bookkeeping + commits, finish, pre-pass, walk summed
+    // over CTAs, [5..8] items those phases worked on (shade, finish, pre-pass, walk), [9] waves,
+    // [10] CTAs
     unsigned long long* profile;
 };
 
-// Shared-memory layout of a CTA: pre-pass program | flat program + triangle records | per warp:
-// control block, pend words, suspended walks, walk masks, the five queues.
+// Shared-memory layout of a CTA: pre-pass program | flat program + triangle records | control
+// block | walk masks | shade lists, finish lists, ray queue, walk queue. Sized by the scene.
 struct SmemLayout {
     uint32_t pre_f4, flat_f4, tri_f4;  // float4 counts
-    uint32_t warp_bytes;
     size_t bytes;
 };
-inline __host__ __device__ SmemLayout smem_layout(const FastScene& sc, uint32_t slots, uint32_t qcap, bool flat) {
-    (void)slots;
+inline __host__ __device__ SmemLayout smem_layout(const FastScene& sc, uint32_t slots, bool flat) {
     SmemLayout l;
     l.pre_f4 = sc.hoisted ? sc.pre_leaves + 2u * sc.pre_boxes + 4u * sc.pre_prims : 0u;
     l.flat_f4 = flat ? kFlatFloat4 : 0u;
     l.tri_f4 = flat ? kTriStride * sc.flat_slots : 0u;
-    uint32_t w = (uint32_t)((sizeof(WarpCtrl) + 15u) & ~(size_t)15u);
-    w += qcap * 4u;                    // pend
-    w += 8u * 32u * 4u;                // suspended walks
-    if (flat) w += 2u * qcap * 4u;     // walk masks
-    w += (3u * qcap + 2u * 2u * qcap) * 2u;  // shade, finish, free | ray, walk queues
-    l.warp_bytes = (w + 15u) & ~15u;
-    l.bytes = (size_t)(l.pre_f4 + l.flat_f4 + l.tri_f4) * 16u + (size_t)l.warp_bytes * kWarps;
+    l.bytes = (size_t)(l.pre_f4 + l.flat_f4 + l.tri_f4) * 16u + ((sizeof(LocalCtrl) + 15u) & ~(size_t)15u) +
+              (flat ? (size_t)2u * slots * 4u : 0u) + (size_t)8u * slots * 2u;
     return l;
 }
 
@@ -168,19 +158,19 @@ struct PathRegs {
     uint32_t occluded;
 };
 
-struct Warp {
-    WarpCtrl* c;
+struct Cta {
+    LocalCtrl* c;
     const float4* spre;
     const float4* sflat;
     const float4* stri;
-    uint32_t* pend;    // [qcap]
-    uint32_t* susp;    // [8][32]
-    uint32_t* walkm;   // [2 qcap] leaf masks of the walk queue's rays (flat walk)
-    uint16_t* q[Q_COUNT];
-    uint32_t qmask[Q_COUNT];
-    size_t pool;       // first global slot of this warp
-    float4* stage;     // this warp's staging blocks
-    uint32_t lane, lt;  // lane index, mask of the lanes below
+    uint16_t* shadeL;  // [2][S]
+    uint16_t* finL;    // [2][S]
+    uint16_t* rayq;    // [2S]
+    uint16_t* walkq;   // [2S]
+    uint32_t* walkm;   // [2S] leaf masks of the walk queue's rays (flat walk)
+    size_t pool;       // first global slot of this CTA
+    float4* stage;     // this CTA's staging blocks
+    uint32_t lane, warp;
 };
 
 RT_DEVONLY void load_path(const LocalParams& p, size_t g, PathRegs& s, uint4& I) {
@@ -210,24 +200,20 @@ RT_DEVONLY void settle_shadow(PathRegs& s) {
     s.flags = 0u;
 }
 
-// Appends one entry per requesting lane; `tail` is the warp-uniform running index of the queue,
-// kept in a register for the length of a batch. Every lane of the warp must call it.
-RT_DEVONLY uint32_t push(const Warp& k, Queue q, uint32_t& tail, bool want, uint32_t entry) {
-    const unsigned m = __ballot_sync(kFull, want);
-    const uint32_t at = tail + (uint32_t)__popc(m & k.lt);
-    if (want) k.q[q][at & k.qmask[q]] = (uint16_t)entry;
-    tail += (uint32_t)__popc(m);
-    return at;
+// Appends one entry per requesting lane to a shared-memory list with one atomic per warp.
+// Every lane of the warp must call it.
+RT_DEVONLY uint32_t reserve(uint32_t* count, bool want, uint32_t lane) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
+    if (!m) return 0u;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
 }
-
-// One ray of `slot` is settled. Returns where the slot goes when it was the last one:
-// 0 = rays still out, 1 = shade, 2 = finish.
-RT_DEVONLY uint32_t settle(const Warp& k, uint32_t slot, bool found) {
-    const uint32_t delta = (found ? kPendHit : 0u) + 0xFFFFFFFFu;
-    const uint32_t now = atomicAdd(&k.pend[slot], delta) + delta;
-    if (now & kPendCount) return 0u;
-    if (now & kPendDone) return 2u;
-    return (now & kPendHit) ? 1u : 2u;
+RT_DEVONLY void push(uint16_t* list, uint32_t* count, bool want, uint32_t entry, uint32_t lane) {
+    const uint32_t at = reserve(count, want, lane);
+    if (want) list[at] = (uint16_t)entry;
 }
 
 // What the pre-pass leaves for the walk.
@@ -241,7 +227,7 @@ struct PreOut {
 
 // The analytic pre-pass of one ray and the decision whether it needs the walk.
 template <bool FLAT>
-RT_DEVONLY void pre_ray(const LocalParams& p, const Warp& k, const RayCtx& r, bool shadow, PreOut<FLAT>& out) {
+RT_DEVONLY void pre_ray(const LocalParams& p, const Cta& k, const RayCtx& r, bool shadow, PreOut<FLAT>& out) {
     prepass(p.scene, k.spre, r, out.best, out.fb);
     if (FLAT) {
         const float limit = fminf(RT_INFINITY, out.best.t * 1.001f);
@@ -258,264 +244,235 @@ RT_DEVONLY void pre_ray(const LocalParams& p, const Warp& k, const RayCtx& r, bo
     if (shadow && out.best.rec != kNone) out.walk = false;  // blocked by an analytic primitive
 }
 
-// ---- stage: shade ----
+// ---- phase: shade ----
 template <bool FLAT>
-RT_DEVONLY void batch_shade(const LocalParams& p, const Warp& k, uint32_t& n_rays, uint32_t& n_shadow) {
-    WarpCtrl* c = k.c;
-    const uint32_t head = c->head[Q_SHADE];
-    uint32_t n = c->tail[Q_SHADE] - head;
-    n = n < 32u ? n : 32u;
-    uint32_t t_ray = c->tail[Q_RAY], t_fin = c->tail[Q_FIN];
-    const bool on = k.lane < n;
-    const uint32_t slot = on ? k.q[Q_SHADE][(head + k.lane) & k.qmask[Q_SHADE]] : 0u;
-    const size_t g = k.pool + slot;
-    bool emit_closest = false, emit_shadow = false, fin_now = false;
-    if (on) {
-        PathRegs s;
-        uint4 I;
-        load_path(p, g, s, I);
-        settle_shadow(s);
-        float4 o4, d4;
-        ld8w<0>(&p.rOD[2u * g], o4, d4);
-        const float4 h4 = p.hit[g];
-        FHit hit;
-        hit.t = h4.x;
-        hit.rec = f_as_u(h4.y);
-        hit.u = h4.z;
-        hit.v = h4.w;
-        ShadeOut so;
-        shade_hit(p.scene, p.env, xyz(o4), xyz(d4), hit, s.rng, s.T, s.L, so);
-        I.z++;
-        const bool done = so.done || I.z >= p.max_bounces;
-        s.last_pdf = so.next_pdf;
-        s.pending = so.pending;
-        if (so.want_shadow) {
-            emit_shadow = true;
-            s.flags = kFlagShadow;
-            p.sray_d[g] = make_float4(so.shadow_dir.x, so.shadow_dir.y, so.shadow_dir.z, 0.0f);
-            p.occl[g] = 0;
-            n_shadow++;
+RT_DEVONLY void phase_shade(const LocalParams& p, const Cta& k, uint32_t P, uint32_t& n_rays, uint32_t& n_shadow) {
+    const uint32_t Q = P ^ 1u, S = p.slots;
+    LocalCtrl* c = k.c;
+    const uint32_t n = c->n_shade[P];
+    for (uint32_t base = k.warp * 32u; base < n; base += (uint32_t)kWarps * 32u) {
+        const uint32_t idx = base + k.lane;
+        const bool on = idx < n;
+        const uint32_t slot = on ? k.shadeL[P * S + idx] : 0u;
+        const size_t g = k.pool + slot;
+        bool emit_closest = false, emit_shadow = false, fin_now = false, fin_next = false;
+        if (on) {
+            PathRegs s;
+            uint4 I;
+            load_path(p, g, s, I);
+            settle_shadow(s);
+            float4 o4, d4;
+            ld8w<0>(&p.rOD[2u * g], o4, d4);
+            const float4 h4 = p.hit[g];
+            FHit hit;
+            hit.t = h4.x;
+            hit.rec = f_as_u(h4.y);
+            hit.u = h4.z;
+            hit.v = h4.w;
+            ShadeOut so;
+            shade_hit(p.scene, p.env, xyz(o4), xyz(d4), hit, s.rng, s.T, s.L, so);
+            I.z++;
+            const bool done = so.done || I.z >= p.max_bounces;
+            s.last_pdf = so.next_pdf;
+            s.pending = so.pending;
+            if (so.want_shadow) {
+                emit_shadow = true;
+                s.flags = kFlagShadow;
+                p.sray_d[g] = make_float4(so.shadow_dir.x, so.shadow_dir.y, so.shadow_dir.z, 0.0f);
+                p.occl[g] = 0;
+                n_shadow++;
+            }
+            // Both rays start at the hit point (no offset: shader.wgsl:1249, 1295).
+            const float4 point4 = make_float4(so.point.x, so.point.y, so.point.z, RT_INFINITY);
+            if (done) {
+                // With a shadow ray in flight the sample is finished one wave later.
+                I.w = (I.w & ~0xFFu) | PATH_DONE;
+                fin_next = emit_shadow;
+                fin_now = !emit_shadow;
+                if (emit_shadow) p.rOD[2u * g + 0u] = point4;
+            } else {
+                emit_closest = true;
+                st8<0>(&p.rOD[2u * g], point4, make_float4(so.next_dir.x, so.next_dir.y, so.next_dir.z, u_as_f(kNone)));
+                n_rays++;
+            }
+            store_path(p, g, s, I);
         }
-        // Both rays start at the hit point (no offset: shader.wgsl:1249, 1295).
-        const float4 point4 = make_float4(so.point.x, so.point.y, so.point.z, RT_INFINITY);
-        if (done) {
-            // With a shadow ray in flight the sample is finished when that ray is settled.
-            I.w = (I.w & ~0xFFu) | PATH_DONE;
-            fin_now = !emit_shadow;
-            if (emit_shadow) p.rOD[2u * g + 0u] = point4;
-        } else {
-            emit_closest = true;
-            st8<0>(&p.rOD[2u * g], point4, make_float4(so.next_dir.x, so.next_dir.y, so.next_dir.z, u_as_f(kNone)));
-            n_rays++;
-        }
-        if (emit_closest || emit_shadow)
-            k.pend[slot] = (emit_closest ? 1u : 0u) + (emit_shadow ? 1u : 0u) + (done ? kPendDone : 0u);
-        store_path(p, g, s, I);
-    }
-    push(k, Q_RAY, t_ray, emit_closest, slot);
-    push(k, Q_RAY, t_ray, emit_shadow, slot | kShadow);
-    push(k, Q_FIN, t_fin, fin_now, slot);
-    if (k.lane == 0u) {
-        c->head[Q_SHADE] = head + n;
-        c->tail[Q_RAY] = t_ray;
-        c->tail[Q_FIN] = t_fin;
+        push(k.rayq, &c->n_ray, emit_closest, slot, k.lane);
+        push(k.rayq, &c->n_ray, emit_shadow, slot | kShadow, k.lane);
+        push(k.finL + P * S, &c->n_fin[P], fin_now, slot, k.lane);
+        push(k.finL + Q * S, &c->n_fin[Q], fin_next, slot, k.lane);
     }
 }
 
-// The result of a closest-hit ray that needed no walk (or whose walk found nothing).
-RT_DEVONLY bool store_closest(const LocalParams& p, const RayCtx& r, size_t g, const Fallback& fb, FHit best) {
+// Where a ray that needs no walk goes next, and its result.
+RT_DEVONLY void settle_closest(const LocalParams& p, const RayCtx& r, size_t g, const Fallback& fb, FHit best,
+                               bool& to_shade, bool& to_fin) {
     resolve_fallback(p.scene, r, fb, best);
     p.hit[g] = make_float4(best.t, u_as_f(best.rec), best.u, best.v);
-    return best.rec != kNone;
+    to_shade = best.rec != kNone;
+    to_fin = !to_shade;
 }
 
-// ---- stage: finish (and start the next path) ----
+// ---- phase: finish ----
 template <bool FLAT>
-RT_DEVONLY void batch_finish(const LocalParams& p, const Warp& k, float sin_half_fov, uint32_t& n_paths,
+RT_DEVONLY void phase_finish(const LocalParams& p, const Cta& k, uint32_t P, float sin_half_fov, uint32_t& n_paths,
                              uint32_t& n_rays) {
-    WarpCtrl* c = k.c;
-    const uint32_t h_fin = c->head[Q_FIN], h_free = c->head[Q_FREE];
-    uint32_t n_fin = c->tail[Q_FIN] - h_fin;
-    n_fin = n_fin < 32u ? n_fin : 32u;
-    uint32_t handed = c->handed;
+    const uint32_t Q = P ^ 1u, S = p.slots;
+    LocalCtrl* c = k.c;
+    const uint32_t n = c->n_fin[P];
     const uint32_t limit = c->limit;
-    // idle slots join only while there are paths to hand out
-    uint32_t n_idle = c->tail[Q_FREE] - h_free;
-    {
-        const uint32_t room = 32u - n_fin, avail = limit - handed;
-        n_idle = n_idle < room ? n_idle : room;
-        n_idle = n_idle < avail ? n_idle : avail;
-    }
-    uint32_t t_walk = c->tail[Q_WALK], t_shade = c->tail[Q_SHADE], t_fin = c->tail[Q_FIN], t_free = c->tail[Q_FREE];
-    const bool had_path = k.lane < n_fin;
-    const bool on = k.lane < n_fin + n_idle;
-    uint32_t slot = 0u;
-    if (had_path) slot = k.q[Q_FIN][(h_fin + k.lane) & k.qmask[Q_FIN]];
-    else if (on) slot = k.q[Q_FREE][(h_free + k.lane - n_fin) & k.qmask[Q_FREE]];
-    const size_t g = k.pool + slot;
-    const uint32_t tile_px_mask = (1u << p.tile_shift) - 1u;
-
-    PathRegs s;
-    s.rng = 0u;
-    uint4 I = make_uint4(0u, 0u, 0u, 0u);
-    if (had_path) {
-        float4 d4;
-        load_path(p, g, s, I);
-        d4 = p.rOD[2u * g + 1u];
-        settle_shadow(s);
-        if ((I.w & 0xFFu) == PATH_TRACED) {
-            // shader.wgsl:1222-1231 — the ray escaped into the environment.
-            const V3 d = xyz(d4);
-            float u, v;
-            direction_to_uv(d, u, v);
-            V3 sky = env_bilinear(p.env, u, v);
-            float pdf = env_direction_pdf(p.env, u, v);
-            float w = power_heuristic(s.last_pdf, pdf);
-            s.L = s.L + s.T * sky * w;
+    const bool exhausted = c->exhausted != 0u;
+    const uint32_t eshift = 6u + p.window_shift;
+    const uint32_t emask = (1u << eshift) - 1u;
+    for (uint32_t base = k.warp * 32u; base < n; base += (uint32_t)kWarps * 32u) {
+        const uint32_t idx = base + k.lane;
+        const bool on = idx < n;
+        const uint32_t entry = on ? k.finL[P * S + idx] : kFresh;
+        const uint32_t slot = entry & kSlotMask;
+        const bool had_path = on && !(entry & kFresh);
+        const size_t g = k.pool + slot;
+        PathRegs s;
+        s.rng = 0u;
+        uint4 I = make_uint4(0u, 0u, 0u, 0u);
+        float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (had_path) {
+            load_path(p, g, s, I);
+            d4 = p.rOD[2u * g + 1u];
         }
-        // Park the sample in its window's staging block.
-        const uint32_t rs = (I.w >> 8) & 0xFFu, pix = I.w >> 16;
-        const uint32_t kk = I.y - c->ring[rs].w0;
-        __stcs(&k.stage[((((size_t)rs << p.window_shift) + kk) << p.tile_shift) + pix],
-               make_float4(s.L.x, s.L.y, s.L.z, 0.0f));
-        atomicSub(&c->ring[rs].left, 1u);
-    }
-    // ---- the next path indices: handed out in lane order; an index that names no pixel-sample
-    // (partial tile, short last window) is skipped and the lane draws again ----
-    bool need = on, got = false;
-    uint32_t px = 0, py = 0, sample = 0, rs = 0, pix = 0;
-    const uint32_t eshift = p.tile_shift + p.window_shift;
-    for (;;) {
-        const unsigned m = __ballot_sync(kFull, need);
-        if (!m || handed == limit) break;
-        const uint32_t rank = (uint32_t)__popc(m & k.lt);
-        uint32_t give = (uint32_t)__popc(m);
-        give = give < limit - handed ? give : limit - handed;
-        if (need && rank < give) {
-            const uint32_t h = handed + rank;
-            const uint32_t i = h & ((1u << eshift) - 1u);
-            rs = (h >> eshift) & (p.ring_entries - 1u);
-            const RingEntry& en = c->ring[rs];
-            const uint32_t kk = i >> p.tile_shift;
-            pix = i & tile_px_mask;
-            px = (en.tx << p.tile_w_shift) + (pix & ((1u << p.tile_w_shift) - 1u));
-            py = en.ty * ((1u << p.tile_shift) >> p.tile_w_shift) + (pix >> p.tile_w_shift);
-            if (kk < en.count && px < p.width && py < p.height) {
-                sample = en.w0 + kk;
-                got = true;
-                need = false;
+        // ---- the next path indices: one shared-memory atomic per warp ----
+        uint32_t h = reserve(&c->handed, on, k.lane);
+        if (had_path) {
+            settle_shadow(s);
+            if ((I.w & 0xFFu) == PATH_TRACED) {
+                // shader.wgsl:1222-1231 — the ray escaped into the environment.
+                const V3 d = xyz(d4);
+                float u, v;
+                direction_to_uv(d, u, v);
+                V3 sky = env_bilinear(p.env, u, v);
+                float pdf = env_direction_pdf(p.env, u, v);
+                float w = power_heuristic(s.last_pdf, pdf);
+                s.L = s.L + s.T * sky * w;
+            }
+            // Park the sample in its window's staging block.
+            const uint32_t rs = (I.w >> 8) & 0xFFu, pix = I.w >> 16;
+            const uint32_t kk = I.y - c->ring[rs].w0;
+            __stcs(&k.stage[(((size_t)rs << p.window_shift) + kk) * 64u + pix], make_float4(s.L.x, s.L.y, s.L.z, 0.0f));
+            atomicSub(&c->ring[rs].left, 1u);
+        }
+        bool to_walk = false, to_shade = false, to_fin = false, got = false;
+        uint32_t mask = 0u;
+        if (on) {
+            // Draw until the index names a pixel-sample (indices of partial tiles / of a short
+            // last window name none).
+            uint32_t px = 0, py = 0, sample = 0, rs = 0, pix = 0;
+            while ((int32_t)(h - limit) < 0) {
+                const uint32_t i = h & emask;
+                rs = (h >> eshift) & (p.ring_entries - 1u);
+                const RingEntry& en = c->ring[rs];
+                const uint32_t kk = i >> 6;
+                pix = i & 63u;
+                px = en.tx * 8u + (pix & 7u);
+                py = en.ty * 8u + (pix >> 3);
+                if (kk < en.count && px < p.width && py < p.height) {
+                    sample = en.w0 + kk;
+                    got = true;
+                    break;
+                }
+                h = atomicAdd(&c->handed, 1u);
+            }
+            if (!got) {
+                to_fin = !exhausted;  // try again next wave (as a slot without a path); else retire
+            } else {
+                I.x = py * p.width + px;
+                I.y = sample;
+                I.z = 0u;
+                I.w = PATH_TRACED | (rs << 8) | (pix << 16);
+                V3 o, d;
+                camera_ray(p.camera, sin_half_fov, px, py, p.width, p.height, sample, s.rng, o, d);
+                s.T = v3s(1.f);
+                s.L = v3s(0.f);
+                s.pending = v3s(0.f);
+                s.last_pdf = 1.0f;
+                s.flags = 0u;
+                s.occluded = 0u;
+                const RayCtx r = ray_setup(o, d);
+                PreOut<FLAT> pre;
+                pre_ray<FLAT>(p, k, r, false, pre);
+                to_walk = pre.walk;
+                mask = pre.mask;
+                st8<0>(&p.rOD[2u * g], make_float4(o.x, o.y, o.z, to_walk ? pre.best.t : RT_INFINITY),
+                       make_float4(d.x, d.y, d.z, u_as_f(to_walk ? pre.best.rec : kNone)));
+                if (to_walk) p.fb[g] = make_float2(pre.fb.t, u_as_f(pre.fb.index));
+                else settle_closest(p, r, g, pre.fb, pre.best, to_shade, to_fin);
+                store_path(p, g, s, I);
+                n_paths++;
+                n_rays++;
             }
         }
-        handed += give;
-    }
-    bool to_walk = false, to_shade = false, to_fin = false;
-    uint32_t mask = 0u;
-    if (got) {
-        I.x = py * p.width + px;
-        I.y = sample;
-        I.z = 0u;
-        I.w = PATH_TRACED | (rs << 8) | (pix << 16);
-        V3 o, d;
-        camera_ray(p.camera, sin_half_fov, px, py, p.width, p.height, sample, s.rng, o, d);
-        s.T = v3s(1.f);
-        s.L = v3s(0.f);
-        s.pending = v3s(0.f);
-        s.last_pdf = 1.0f;
-        s.flags = 0u;
-        s.occluded = 0u;
-        const RayCtx r = ray_setup(o, d);
-        PreOut<FLAT> pre;
-        pre_ray<FLAT>(p, k, r, false, pre);
-        to_walk = pre.walk;
-        mask = pre.mask;
-        st8<0>(&p.rOD[2u * g], make_float4(o.x, o.y, o.z, to_walk ? pre.best.t : RT_INFINITY),
-               make_float4(d.x, d.y, d.z, u_as_f(to_walk ? pre.best.rec : kNone)));
-        if (to_walk) {
-            p.fb[g] = make_float2(pre.fb.t, u_as_f(pre.fb.index));
-            k.pend[slot] = 1u;
-        } else {
-            to_shade = store_closest(p, r, g, pre.fb, pre.best);
-            to_fin = !to_shade;
+        {
+            const uint32_t at = reserve(&c->n_walk, to_walk, k.lane);
+            if (to_walk) {
+                k.walkq[at] = (uint16_t)slot;
+                if (FLAT) k.walkm[at] = mask;
+            }
         }
-        store_path(p, g, s, I);
-        n_paths++;
-        n_rays++;
-    }
-    {
-        const uint32_t at = push(k, Q_WALK, t_walk, to_walk, slot);
-        if (FLAT && to_walk) k.walkm[at & k.qmask[Q_WALK]] = mask;
-    }
-    push(k, Q_SHADE, t_shade, to_shade, slot);
-    // The finish queue is read from h_fin + n_fin on, so entries appended here are not the ones
-    // this batch is working on.
-    push(k, Q_FIN, t_fin, to_fin, slot);
-    push(k, Q_FREE, t_free, on && !got, slot);
-    if (k.lane == 0u) {
-        c->head[Q_FIN] = h_fin + n_fin;
-        c->head[Q_FREE] = h_free + n_idle;
-        c->tail[Q_WALK] = t_walk;
-        c->tail[Q_SHADE] = t_shade;
-        c->tail[Q_FIN] = t_fin;
-        c->tail[Q_FREE] = t_free;
-        c->handed = handed;
+        push(k.shadeL + Q * S, &c->n_shade[Q], to_shade, slot, k.lane);
+        // a slot that drew nothing re-enters the finish list without a path
+        push(k.finL + Q * S, &c->n_fin[Q], to_fin, got ? slot : (slot | kFresh), k.lane);
     }
 }
 
-// ---- stage: pre-pass of the rays the shade stage emitted ----
+// ---- phase: pre-pass of the rays the shade phase emitted ----
 template <bool FLAT>
-RT_DEVONLY void batch_prepass(const LocalParams& p, const Warp& k) {
-    WarpCtrl* c = k.c;
-    const uint32_t head = c->head[Q_RAY];
-    uint32_t n = c->tail[Q_RAY] - head;
-    n = n < 32u ? n : 32u;
-    uint32_t t_walk = c->tail[Q_WALK], t_shade = c->tail[Q_SHADE], t_fin = c->tail[Q_FIN];
-    const bool on = k.lane < n;
-    const uint32_t e = on ? k.q[Q_RAY][(head + k.lane) & k.qmask[Q_RAY]] : 0u;
-    const uint32_t slot = e & kSlotMask;
-    const bool shadow = (e & kShadow) != 0u;
-    const size_t g = k.pool + slot;
-    bool to_walk = false;
-    uint32_t route = 0u, mask = 0u;
-    if (on) {
-        const V3 o = xyz(p.rOD[2u * g + 0u]);
-        const V3 d = xyz(shadow ? p.sray_d[g] : p.rOD[2u * g + 1u]);
-        const RayCtx r = ray_setup(o, d);
-        PreOut<FLAT> pre;
-        pre_ray<FLAT>(p, k, r, shadow, pre);
-        to_walk = pre.walk;
-        mask = pre.mask;
-        if (shadow) {
-            if (pre.best.rec != kNone) p.occl[g] = 1;
-            if (!to_walk) route = settle(k, slot, false);
-        } else if (to_walk) {
-            p.rOD[2u * g + 0u].w = pre.best.t;
-            p.rOD[2u * g + 1u].w = u_as_f(pre.best.rec);
-            p.fb[g] = make_float2(pre.fb.t, u_as_f(pre.fb.index));
-        } else {
-            route = settle(k, slot, store_closest(p, r, g, pre.fb, pre.best));
+RT_DEVONLY void phase_prepass(const LocalParams& p, const Cta& k, uint32_t P) {
+    const uint32_t Q = P ^ 1u, S = p.slots;
+    LocalCtrl* c = k.c;
+    const uint32_t n = c->n_ray;
+    for (uint32_t base = k.warp * 32u; base < n; base += (uint32_t)kWarps * 32u) {
+        const uint32_t idx = base + k.lane;
+        const bool on = idx < n;
+        const uint32_t e = on ? k.rayq[idx] : 0u;
+        const uint32_t slot = e & kSlotMask;
+        const bool shadow = (e & kShadow) != 0u;
+        const size_t g = k.pool + slot;
+        bool to_walk = false, to_shade = false, to_fin = false;
+        uint32_t mask = 0u;
+        if (on) {
+            const V3 o = xyz(p.rOD[2u * g + 0u]);
+            const V3 d = xyz(shadow ? p.sray_d[g] : p.rOD[2u * g + 1u]);
+            const RayCtx r = ray_setup(o, d);
+            PreOut<FLAT> pre;
+            pre_ray<FLAT>(p, k, r, shadow, pre);
+            to_walk = pre.walk;
+            mask = pre.mask;
+            if (shadow) {
+                if (pre.best.rec != kNone) p.occl[g] = 1;
+            } else if (to_walk) {
+                p.rOD[2u * g + 0u].w = pre.best.t;
+                p.rOD[2u * g + 1u].w = u_as_f(pre.best.rec);
+                p.fb[g] = make_float2(pre.fb.t, u_as_f(pre.fb.index));
+            } else {
+                settle_closest(p, r, g, pre.fb, pre.best, to_shade, to_fin);
+            }
         }
-    }
-    {
-        const uint32_t at = push(k, Q_WALK, t_walk, to_walk, e);
-        if (FLAT && to_walk) k.walkm[at & k.qmask[Q_WALK]] = mask;
-    }
-    push(k, Q_SHADE, t_shade, route == 1u, slot);
-    push(k, Q_FIN, t_fin, route == 2u, slot);
-    if (k.lane == 0u) {
-        c->head[Q_RAY] = head + n;
-        c->tail[Q_WALK] = t_walk;
-        c->tail[Q_SHADE] = t_shade;
-        c->tail[Q_FIN] = t_fin;
+        {
+            const uint32_t at = reserve(&c->n_walk, to_walk, k.lane);
+            if (to_walk) {
+                k.walkq[at] = (uint16_t)e;
+                if (FLAT) k.walkm[at] = mask;
+            }
+        }
+        push(k.shadeL + Q * S, &c->n_shade[Q], to_shade, slot, k.lane);
+        push(k.finL + Q * S, &c->n_fin[Q], to_fin, slot, k.lane);
     }
 }
 
-// A walked ray's result. Returns the slot's route (see settle()).
-RT_DEVONLY uint32_t walk_result(const LocalParams& p, const Warp& k, const RayCtx& r, uint32_t slot, bool any_hit,
-                                FHit best) {
-    const size_t g = k.pool + slot;
+// A walked ray's result: closest-hit rays move to the shade or finish list of the next wave.
+RT_DEVONLY void walk_result(const LocalParams& p, const RayCtx& r, size_t g, bool any_hit, FHit best, bool& to_shade,
+                            bool& to_fin) {
     if (any_hit) {
         if (best.rec != kNone) p.occl[g] = 1;
-        return settle(k, slot, false);
+        return;
     }
     if (best.rec == kNone) {
         const float2 f = p.fb[g];
@@ -525,21 +482,19 @@ RT_DEVONLY uint32_t walk_result(const LocalParams& p, const Warp& k, const RayCt
         resolve_fallback(p.scene, r, fb, best);
     }
     p.hit[g] = make_float4(best.t, u_as_f(best.rec), best.u, best.v);
-    return settle(k, slot, best.rec != kNone);
+    to_shade = best.rec != kNone;
+    to_fin = !to_shade;
 }
 
-// ---- stage: walk. Persistent lanes; a lane whose ray is finished takes the next entry. With
-// `flush` the batch runs until queue and lanes are empty; otherwise it leaves once the queue is
-// empty and fewer than kMinBusy lanes still walk, parking those lanes' state for the next batch.
+// ---- phase: walk. Persistent lanes; a lane whose ray is finished takes the next entry. ----
 template <bool FLAT>
-RT_DEVONLY void batch_walk(const LocalParams& p, const Warp& k, uint2* stack, bool flush) {
-    WarpCtrl* c = k.c;
-    uint32_t head = c->head[Q_WALK];
-    const uint32_t total = c->tail[Q_WALK];
-    uint32_t t_shade = c->tail[Q_SHADE], t_fin = c->tail[Q_FIN];
+RT_DEVONLY void phase_walk(const LocalParams& p, const Cta& k, uint32_t P) {
+    const uint32_t Q = P ^ 1u, S = p.slots;
+    LocalCtrl* c = k.c;
+    const uint32_t total = c->n_walk;
     const uint32_t lane = k.lane;
 
-    bool busy = false, any_hit = false;
+    bool busy = false, any_hit = false, drained = false;
     uint32_t slot = 0;
     RayCtx r = ray_setup(v3s(0.f), v3s(1.f));
     FHit best;
@@ -554,70 +509,42 @@ RT_DEVONLY void batch_walk(const LocalParams& p, const Warp& k, uint2* stack, bo
     w.cur = kNone;
     w.sp = 0u;
     w.limit = RT_INFINITY;
-
-    // ---- resume the walks the last batch parked (each lane its own: the stack never moved) ----
-    if (c->n_susp) {
-        const uint32_t tag = k.susp[lane];
-        if (tag != kNone) {
-            slot = tag & kSlotMask;
-            any_hit = (tag & kShadow) != 0u;
-            const size_t g = k.pool + slot;
-            const float4 o4 = p.rOD[2u * g + 0u];
-            const float4 d4 = any_hit ? p.sray_d[g] : p.rOD[2u * g + 1u];
-            r = ray_setup(xyz(o4), xyz(d4));
-            best.t = u_as_f(k.susp[32u + lane]);
-            best.rec = k.susp[64u + lane];
-            best.u = u_as_f(k.susp[96u + lane]);
-            best.v = u_as_f(k.susp[128u + lane]);
-            const uint32_t a = k.susp[160u + lane], b = k.susp[192u + lane];
-            const float l = u_as_f(k.susp[224u + lane]);
-            if (FLAT) {
-                mask = a;
-                cur = b & 0xFFFFu;
-                end = b >> 16;
-                limit = l;
-            } else {
-                w.cur = a;
-                w.sp = b;
-                w.limit = l;
-            }
-            busy = true;
-        }
-    }
+    uint2 stack[FLAT ? 1 : kStackCap];
 
     for (;;) {
         // ---- refill: idle lanes take the next entries ----
-        const unsigned idle = __ballot_sync(kFull, !busy);
-        if (idle && head != total) {
-            uint32_t take = (uint32_t)__popc(idle);
-            take = take < total - head ? take : total - head;
-            const uint32_t rank = (uint32_t)__popc(idle & k.lt);
-            if (!busy && rank < take) {
-                const uint32_t idx = (head + rank) & k.qmask[Q_WALK];
-                const uint32_t e = k.q[Q_WALK][idx];
-                slot = e & kSlotMask;
-                any_hit = (e & kShadow) != 0u;
-                const size_t g = k.pool + slot;
-                const float4 o4 = p.rOD[2u * g + 0u];
-                const float4 d4 = any_hit ? p.sray_d[g] : p.rOD[2u * g + 1u];
-                r = ray_setup(xyz(o4), xyz(d4));
-                best.t = any_hit ? RT_INFINITY : o4.w;
-                best.rec = any_hit ? kNone : f_as_u(d4.w);
-                best.u = best.v = 0.0f;
-                if (FLAT) {
-                    mask = k.walkm[idx];
-                    cur = end = 0u;
-                    limit = fminf(RT_INFINITY, best.t * 1.001f);
-                } else {
-                    walk_begin(p.scene, true, 0.0f, best, w);  // the pre-pass checked the root box
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
+        if (idle && !drained) {
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(&c->walk_head, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (base + (uint32_t)__popc(idle) >= total) drained = true;
+            if (!busy) {
+                const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < total) {
+                    const uint32_t e = k.walkq[idx];
+                    slot = e & kSlotMask;
+                    any_hit = (e & kShadow) != 0u;
+                    const size_t g = k.pool + slot;
+                    const float4 o4 = p.rOD[2u * g + 0u];
+                    const float4 d4 = any_hit ? p.sray_d[g] : p.rOD[2u * g + 1u];
+                    r = ray_setup(xyz(o4), xyz(d4));
+                    best.t = any_hit ? RT_INFINITY : o4.w;
+                    best.rec = any_hit ? kNone : f_as_u(d4.w);
+                    best.u = best.v = 0.0f;
+                    if (FLAT) {
+                        mask = k.walkm[idx];
+                        cur = end = 0u;
+                        limit = fminf(RT_INFINITY, best.t * 1.001f);
+                    } else {
+                        walk_begin(p.scene, true, 0.0f, best, w);  // the pre-pass checked the root box
+                    }
+                    busy = true;
                 }
-                busy = true;
             }
-            head += take;
         }
-        const uint32_t walking = (uint32_t)__popc(__ballot_sync(kFull, busy));
-        if (!walking) break;
-        if (!flush && head == total && walking < kMinBusy) break;
+        if (!__any_sync(0xFFFFFFFFu, busy)) break;  // nothing was handed out: the queue is empty
 
         bool settled = false, finished = false;
         if (FLAT) {
@@ -648,7 +575,7 @@ RT_DEVONLY void batch_walk(const LocalParams& p, const Warp& k, uint2* stack, bo
             }
             finished = busy && (settled || (cur == end && mask == 0u));
         } else {
-            if (__all_sync(kFull, !busy || r.plain)) {
+            if (__all_sync(0xFFFFFFFFu, !busy || r.plain)) {
                 while (busy && w.cur < kLeafBit) walk_node<true>(p.scene, r, w, stack);
             } else {
                 while (busy && w.cur < kLeafBit) walk_node<false>(p.scene, r, w, stack);
@@ -658,38 +585,21 @@ RT_DEVONLY void batch_walk(const LocalParams& p, const Warp& k, uint2* stack, bo
         }
 
         // ---- lanes whose ray is finished hand over their result ----
-        uint32_t route = 0u;
+        bool to_shade = false, to_fin = false;
         if (finished) {
-            route = walk_result(p, k, r, slot, any_hit, best);
+            walk_result(p, r, k.pool + slot, any_hit, best, to_shade, to_fin);
             busy = false;
         }
-        push(k, Q_SHADE, t_shade, route == 1u, slot);
-        push(k, Q_FIN, t_fin, route == 2u, slot);
-    }
-
-    // ---- park what is still walking ----
-    const unsigned left = __ballot_sync(kFull, busy);
-    k.susp[lane] = busy ? (slot | (any_hit ? kShadow : 0u)) : kNone;
-    if (busy) {
-        k.susp[32u + lane] = f_as_u(best.t);
-        k.susp[64u + lane] = best.rec;
-        k.susp[96u + lane] = f_as_u(best.u);
-        k.susp[128u + lane] = f_as_u(best.v);
-        k.susp[160u + lane] = FLAT ? mask : w.cur;
-        k.susp[192u + lane] = FLAT ? (cur | (end << 16)) : w.sp;
-        k.susp[224u + lane] = f_as_u(FLAT ? limit : w.limit);
-    }
-    if (lane == 0u) {
-        c->n_susp = (uint32_t)__popc(left);
-        c->head[Q_WALK] = head;
-        c->tail[Q_SHADE] = t_shade;
-        c->tail[Q_FIN] = t_fin;
+        push(k.shadeL + Q * S, &c->n_shade[Q], to_shade, slot, lane);
+        push(k.finL + Q * S, &c->n_fin[Q], to_fin, slot, lane);
     }
 }
 
-// ---- window bookkeeping, by lane 0 ----
-RT_DEVONLY void maintain(const LocalParams& p, WarpCtrl* c) {
-    const uint32_t E = 1u << (p.tile_shift + p.window_shift);
+// ---- window bookkeeping, by thread 0 between the shade and the finish phase ----
+RT_DEVONLY void maintain(const LocalParams& p, LocalCtrl* c) {
+    const uint32_t E = 64u << p.window_shift;
+    // the handout may have run past the open windows; those indices went to nobody
+    if ((int32_t)(c->handed - c->limit) > 0) c->handed = c->limit;
     // windows whose paths are all in, oldest first
     c->commit_n = 0u;
     while (c->ring_head != c->ring_tail && c->commit_n < kMaxCommit) {
@@ -700,9 +610,8 @@ RT_DEVONLY void maintain(const LocalParams& p, WarpCtrl* c) {
         c->commit_n++;
         c->ring_head++;
     }
-    // open windows until every slot could draw a path
+    // open windows until every slot could draw a path in the coming finish phase
     const uint32_t W = 1u << p.window_shift;
-    const uint32_t tile_w = 1u << p.tile_w_shift, tile_h = (1u << p.tile_shift) >> p.tile_w_shift;
     while (!c->exhausted && c->ring_tail - c->ring_head < p.ring_entries && c->limit - c->handed < p.slots) {
         if (!c->tile_valid) {
             if (c->tile_next == c->tile_end) {
@@ -720,17 +629,14 @@ RT_DEVONLY void maintain(const LocalParams& p, WarpCtrl* c) {
             c->next_window = 0u;
             c->tile_valid = 1u;
         }
-        // a window is a block of E consecutive virtual path indices: the handout must stand at
-        // the block's first index when the window before it was cut short by nothing — it never
-        // is: indices past a window's real paths are drawn and skipped (batch_finish)
         RingEntry& e = c->ring[c->ring_tail & (p.ring_entries - 1u)];
         e.tx = c->cur_tx;
         e.ty = c->cur_ty;
         const uint32_t first = c->next_window * W;
         e.w0 = p.sample_begin + first;
         e.count = p.sample_count - first < W ? p.sample_count - first : W;
-        const uint32_t vw = p.width - e.tx * tile_w < tile_w ? p.width - e.tx * tile_w : tile_w;
-        const uint32_t vh = p.height - e.ty * tile_h < tile_h ? p.height - e.ty * tile_h : tile_h;
+        const uint32_t vw = p.width - e.tx * 8u < 8u ? p.width - e.tx * 8u : 8u;
+        const uint32_t vh = p.height - e.ty * 8u < 8u ? p.height - e.ty * 8u : 8u;
         e.left = e.count * vw * vh;
         c->next_window++;
         if (c->next_window * W >= p.sample_count) c->tile_valid = 0u;
@@ -740,77 +646,64 @@ RT_DEVONLY void maintain(const LocalParams& p, WarpCtrl* c) {
 }
 
 // Adds the staged planes of the windows in c->commit to the accumulation buffer, in sample
-// order (shader.wgsl:1367-1371: total += sample, alpha = 1). The same lane owns a pixel in every
-// window of a tile, and windows are committed in the order they were opened.
-RT_DEVONLY void commit_windows(const LocalParams& p, const Warp& k) {
+// order (shader.wgsl:1367-1371: total += sample, alpha = 1). Thread t < 64 owns pixel t of every
+// tile, so two windows of one tile are added in the order they were opened.
+RT_DEVONLY void commit_windows(const LocalParams& p, const Cta& k) {
+    const uint32_t pix = threadIdx.x;
+    if (pix >= 64u) return;
     const uint32_t n = k.c->commit_n;
-    const uint32_t tile_px = 1u << p.tile_shift;
-    const uint32_t tile_h = tile_px >> p.tile_w_shift;
     for (uint32_t j = 0; j < n; j++) {
         const RingEntry& e = k.c->commit[j];
-        for (uint32_t pix = k.lane; pix < tile_px; pix += 32u) {
-            const uint32_t px = (e.tx << p.tile_w_shift) + (pix & ((1u << p.tile_w_shift) - 1u));
-            const uint32_t py = e.ty * tile_h + (pix >> p.tile_w_shift);
-            if (px >= p.width || py >= p.height) continue;
-            float4* at = &p.accum[(size_t)py * p.width + px];
-            float4 a = *at;
-            const float4* plane = k.stage + ((((size_t)e.pad[0] << p.window_shift)) << p.tile_shift) + pix;
-            for (uint32_t s = 0; s < e.count; s++) {
-                const float4 v = __ldcs(plane + ((size_t)s << p.tile_shift));
-                a.x = a.x + v.x;
-                a.y = a.y + v.y;
-                a.z = a.z + v.z;
-            }
-            a.w = 1.0f;
-            *at = a;
+        const uint32_t px = e.tx * 8u + (pix & 7u), py = e.ty * 8u + (pix >> 3);
+        if (px >= p.width || py >= p.height) continue;
+        float4* at = &p.accum[(size_t)py * p.width + px];
+        float4 a = *at;
+        const float4* plane = k.stage + (((size_t)e.pad[0] << p.window_shift) * 64u + pix);
+        for (uint32_t s = 0; s < e.count; s++) {
+            const float4 v = __ldcs(plane + (size_t)s * 64u);
+            a.x = a.x + v.x;
+            a.y = a.y + v.y;
+            a.z = a.z + v.z;
         }
+        a.w = 1.0f;
+        *at = a;
     }
 }
 
 template <bool FLAT>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) local_wave_kernel(const LocalParams p) {
     extern __shared__ float4 smem[];
-    const SmemLayout lay = smem_layout(p.scene, p.slots, p.qcap, FLAT);
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    Warp k;
+    Cta k;
+    const SmemLayout lay = smem_layout(p.scene, p.slots, FLAT);
     {
-        const float4* q = smem;
+        float4* q = smem;
         k.spre = q;
         q += lay.pre_f4;
         k.sflat = q;
         q += lay.flat_f4;
         k.stri = q;
         q += lay.tri_f4;
-        char* b = (char*)q + (size_t)warp * lay.warp_bytes;
-        k.c = (WarpCtrl*)b;
-        b += (sizeof(WarpCtrl) + 15u) & ~(size_t)15u;
-        k.pend = (uint32_t*)b;
-        b += p.qcap * 4u;
-        k.susp = (uint32_t*)b;
-        b += 8u * 32u * 4u;
-        k.walkm = (uint32_t*)b;
-        if (FLAT) b += 2u * p.qcap * 4u;
-        uint16_t* h = (uint16_t*)b;
-        k.q[Q_SHADE] = h;
-        h += p.qcap;
-        k.q[Q_FIN] = h;
-        h += p.qcap;
-        k.q[Q_FREE] = h;
-        h += p.qcap;
-        k.q[Q_RAY] = h;
-        h += 2u * p.qcap;
-        k.q[Q_WALK] = h;
-        k.qmask[Q_SHADE] = k.qmask[Q_FIN] = k.qmask[Q_FREE] = p.qcap - 1u;
-        k.qmask[Q_RAY] = k.qmask[Q_WALK] = 2u * p.qcap - 1u;
+        k.c = (LocalCtrl*)q;
+        q += (sizeof(LocalCtrl) + 15u) / 16u;
+        uint32_t* u = (uint32_t*)q;
+        k.walkm = u;
+        if (FLAT) u += 2u * p.slots;
+        uint16_t* h = (uint16_t*)u;
+        k.shadeL = h;
+        h += 2u * p.slots;
+        k.finL = h;
+        h += 2u * p.slots;
+        k.rayq = h;
+        h += 2u * p.slots;
+        k.walkq = h;
     }
-    const size_t gwarp = (size_t)blockIdx.x * kWarps + warp;
-    k.pool = gwarp * p.slots;
-    k.stage = p.staging + gwarp * ((((size_t)p.ring_entries << p.window_shift)) << p.tile_shift);
-    k.lane = lane;
-    k.lt = (1u << lane) - 1u;
-    WarpCtrl* c = k.c;
+    k.pool = (size_t)blockIdx.x * p.slots;
+    k.stage = p.staging + (size_t)blockIdx.x * (((size_t)p.ring_entries << p.window_shift) * 64u);
+    k.lane = threadIdx.x & 31u;
+    k.warp = threadIdx.x >> 5;
+    const uint32_t S = p.slots;
 
-    // ---- set-up: scene programs into shared memory (the one CTA-wide step), every slot idle ----
+    // ---- set-up: scene programs into shared memory, every slot starts without a path ----
     {
         float4* spre = smem;
         for (uint32_t i = threadIdx.x; i < lay.pre_f4; i += kThreads) spre[i] = p.scene.pre[i];
@@ -820,111 +713,92 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) local_wave_kernel(const 
             float4* stri = sflat + lay.flat_f4;
             for (uint32_t i = threadIdx.x; i < lay.tri_f4; i += kThreads) stri[i] = p.scene.tri[i];
         }
-        for (uint32_t i = lane; i < p.slots; i += 32u) k.q[Q_FREE][i] = (uint16_t)i;
-        k.susp[lane] = kNone;
-        if (lane == 0u) {
-            for (uint32_t i = 0; i < Q_COUNT; i++) c->head[i] = c->tail[i] = 0u;
-            c->tail[Q_FREE] = p.slots;
+        for (uint32_t i = threadIdx.x; i < S; i += kThreads) k.finL[i] = (uint16_t)(i | kFresh);
+        if (threadIdx.x == 0) {
+            LocalCtrl* c = k.c;
+            c->n_shade[0] = c->n_shade[1] = 0u;
+            c->n_fin[0] = S;
+            c->n_fin[1] = 0u;
+            c->n_ray = c->n_walk = c->walk_head = 0u;
             c->handed = c->limit = 0u;
             c->ring_head = c->ring_tail = 0u;
             c->tile_next = c->tile_end = 0u;
             c->tile_valid = 0u;
             c->cur_tx = c->cur_ty = c->next_window = 0u;
             c->exhausted = 0u;
-            c->n_susp = 0u;
             c->commit_n = 0u;
-            for (int i = 0; i < 5; i++) c->cycles[i] = 0ull;
-            for (int i = 0; i < 4; i++) c->items[i] = c->batches[i] = 0ull;
+            c->quit = 0u;
         }
     }
     __syncthreads();
 
     const float sin_half_fov = rt_sin(p.camera.fov_y / 2.0f);
     uint32_t n_paths = 0, n_rays = 0, n_shadow = 0;
-    uint2 stack[FLAT ? 1 : kStackCap];
-    const bool prof = p.profile != nullptr;
-    unsigned long long t_last = prof ? clock64() : 0ull;
-    auto lap = [&](int what, uint32_t items) {  // lane 0 keeps the books
-        if (lane == 0u) {
-            const unsigned long long now = clock64();
-            c->cycles[what] += now - t_last;
-            t_last = now;
-            if (what < 4) {
-                c->items[what] += items;
-                c->batches[what]++;
-            }
-        }
-    };
+    LocalCtrl* c = k.c;
 
-    uint32_t stall = 0u;
+    const bool prof = p.profile != nullptr;
+    auto lap = [&](int phase) {  // thread 0, right after a barrier
+        const unsigned long long now = clock64();
+        c->cycles[phase] += now - c->t_last;
+        c->t_last = now;
+    };
+    if (prof && threadIdx.x == 0) {
+        for (int i = 0; i < 5; i++) c->cycles[i] = 0ull;
+        for (int i = 0; i < 4; i++) c->items[i] = 0ull;
+        c->waves = 0ull;
+        c->t_last = clock64();
+    }
+    for (uint32_t P = 0;; P ^= 1u) {
+        phase_shade<FLAT>(p, k, P, n_rays, n_shadow);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (prof) lap(0);
+            maintain(p, c);
+        }
+        __syncthreads();
+        commit_windows(p, k);  // reads staging blocks the coming finish phase may reuse
+        __syncthreads();
+        if (prof && threadIdx.x == 0) lap(1);
+        phase_finish<FLAT>(p, k, P, sin_half_fov, n_paths, n_rays);
+        __syncthreads();
+        if (prof && threadIdx.x == 0) lap(2);
+        phase_prepass<FLAT>(p, k, P);
+        __syncthreads();
+        if (prof && threadIdx.x == 0) lap(3);
+        phase_walk<FLAT>(p, k, P);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (prof) {
+                lap(4);
+                c->items[0] += c->n_shade[P];
+                c->items[1] += c->n_fin[P];
+                c->items[2] += c->n_ray;
+                c->items[3] += c->n_walk;
+                c->waves++;
+            }
+            c->n_shade[P] = 0u;
+            c->n_fin[P] = 0u;
+            c->n_ray = c->n_walk = c->walk_head = 0u;
+            // every slot with a path (or waiting for one) is on a list of the next wave
+            c->quit = (c->n_shade[P ^ 1u] + c->n_fin[P ^ 1u]) == 0u ? 1u : 0u;
+        }
+        __syncthreads();
+        if (c->quit) break;
+    }
+    // the windows still waiting for their commit (all their paths are in)
     for (;;) {
-        __syncwarp();
-        // ---- windows: commit the finished ones, open new ones while slots could use more paths ----
-        {
-            const bool can_commit = c->ring_head != c->ring_tail && c->ring[c->ring_head & (p.ring_entries - 1u)].left == 0u;
-            const bool can_open = !c->exhausted && c->ring_tail - c->ring_head < p.ring_entries &&
-                                  c->limit - c->handed < p.slots;
-            if (can_commit || can_open) {
-                if (lane == 0u) maintain(p, c);
-                __syncwarp();
-                commit_windows(p, k);  // reads staging blocks the coming finish batches may reuse
-                __syncwarp();
-            }
-        }
-        const uint32_t n_shade = c->tail[Q_SHADE] - c->head[Q_SHADE], n_fin = c->tail[Q_FIN] - c->head[Q_FIN];
-        const uint32_t n_free = c->tail[Q_FREE] - c->head[Q_FREE], n_ray = c->tail[Q_RAY] - c->head[Q_RAY];
-        const uint32_t n_walk = c->tail[Q_WALK] - c->head[Q_WALK] + c->n_susp;
-        const uint32_t avail = c->limit - c->handed;
-        const uint32_t n_spawn = n_fin + (n_free < avail ? n_free : avail);
-        if (prof) lap(4, 0u);
-        int stage;
-        if (n_walk >= 32u) stage = 3;
-        else if (n_ray >= 32u) stage = 2;
-        else if (n_shade >= 32u) stage = 0;
-        else if (n_spawn >= 32u) stage = 1;
-        else {
-            // nothing fills a batch: the fullest stage, the walk run to its end
-            uint32_t most = n_walk;
-            stage = 3;
-            if (n_ray > most) most = n_ray, stage = 2;
-            if (n_shade > most) most = n_shade, stage = 0;
-            if (n_spawn > most) most = n_spawn, stage = 1;
-            if (most == 0u) {
-                if (c->exhausted && c->ring_head == c->ring_tail) break;  // every window is committed
-                if (++stall > kStallLimit) {
-                    if (lane == 0u) atomicExch(p.error, 1u);
-                    break;
-                }
-                continue;
-            }
-            if (stage == 3) stage = 4;  // flush
-        }
-        stall = 0u;
-        switch (stage) {
-            case 0:
-                batch_shade<FLAT>(p, k, n_rays, n_shadow);
-                if (prof) lap(0, n_shade < 32u ? n_shade : 32u);
-                break;
-            case 1:
-                batch_finish<FLAT>(p, k, sin_half_fov, n_paths, n_rays);
-                if (prof) lap(1, n_spawn < 32u ? n_spawn : 32u);
-                break;
-            case 2:
-                batch_prepass<FLAT>(p, k);
-                if (prof) lap(2, n_ray < 32u ? n_ray : 32u);
-                break;
-            default:
-                batch_walk<FLAT>(p, k, stack, stage == 4);
-                if (prof) lap(3, n_walk - (c->tail[Q_WALK] - c->head[Q_WALK] + c->n_susp));
-                break;
-        }
+        if (threadIdx.x == 0) maintain(p, c);
+        __syncthreads();
+        if (c->commit_n == 0u) break;
+        commit_windows(p, k);
+        __syncthreads();
     }
     fast_flush_counts(n_paths, n_rays, n_shadow, p.counters);
-    if (prof && lane == 0u) {
+    if (prof && threadIdx.x == 0) {
         for (int i = 0; i < 5; i++) atomicAdd(&p.profile[i], c->cycles[i]);
         for (int i = 0; i < 4; i++) atomicAdd(&p.profile[5 + i], c->items[i]);
-        for (int i = 0; i < 4; i++) atomicAdd(&p.profile[9 + i], c->batches[i]);
-        atomicAdd(&p.profile[13], 1ull);
+        atomicAdd(&p.profile[9], c->waves);
+        atomicAdd(&p.profile[10], 1ull);
     }
 }
 

@@ -33,7 +33,7 @@ def test_all_kernels_agree_bit_for_bit(rt, house, env_small, monkeypatch):
     w, h = 200, 112
     images = {}
     for kernel in ("local", "wave", "fast", "pixel"):
-        monkeypatch.setenv("RT_KERNEL", kernel)
+        monkeypatch.setenv("RT_KERNEL", kernel)  # "wave" is the default (the product path)
         st, images[kernel] = _render(rt, house, env_small, w, h, 3, 8)
         c = st.counters()
         assert c["paths"] == w * h * 3
@@ -42,15 +42,16 @@ def test_all_kernels_agree_bit_for_bit(rt, house, env_small, monkeypatch):
     assert images["local_counts"] == images["wave_counts"] == images["fast_counts"] == images["pixel_counts"]
 
 
-@pytest.mark.parametrize("slots,window,w,h,spp", [(32, 1, 203, 117, 5), (64, 4, 320, 180, 9), (128, 16, 161, 90, 20),
-                                                  (256, 2, 161, 90, 4), (96, 8, 97, 61, 11), (128, 4, 640, 360, 3)])
-def test_local_pools_windows_and_rings(rt, orc, house, env_small, monkeypatch, slots, window, w, h, spp):
-    # The persistent kernel with tiny pools (every slot traces many paths), one-sample windows
-    # (the slots wait for commits all the time), windows that do not divide the sample count, pools
-    # that are no power of two, sizes with partial tiles, 4x4 and 8x4 tiles: the image must not
-    # depend on any of it.
+@pytest.mark.parametrize("slots,stage,window,w,h,spp", [(64, 64, 1, 203, 117, 5), (256, 1024, 4, 320, 180, 9),
+                                                        (1024, 8192, 16, 161, 90, 20), (4096, 65536, 16, 161, 90, 4),
+                                                        (512, 2048, 8, 97, 61, 11)])
+def test_local_pools_windows_and_rings(rt, orc, house, env_small, monkeypatch, slots, stage, window, w, h, spp):
+    # The persistent kernel with tiny pools (every slot traces many paths), a one-window ring
+    # (stage = 64 * window: the slots wait for every commit), windows that do not divide the
+    # sample count, sizes with partial 8x8 tiles: the image must not depend on any of it.
     monkeypatch.setenv("RT_KERNEL", "local")
     monkeypatch.setenv("RT_LOCAL_SLOTS", str(slots))
+    monkeypatch.setenv("RT_LOCAL_STAGE", str(stage))
     monkeypatch.setenv("RT_LOCAL_WINDOW", str(window))
     st, got = _render(rt, house, env_small, w, h, spp, 8, begin=3)
     want, counters = orc.Oracle(house, env_small, w, h, max_bounces=8).render(3, spp)
