@@ -131,7 +131,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_SAMPLER_MS", "100")],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -368,7 +368,7 @@ def main():
             scaling = "strong"
         else:
             sample_begin, count = rt.samplesplit.weak_range(spp, rank)
-            scaling = "weak"
+            scaling = "weak" if world > 1 else args.scaling   # one GPU: the two modes are the same run
 
         # The accumulation buffer is a torch tensor so the NCCL reduce can run on it, and the
         # backend launches on torch's current stream so torch events bracket its kernels.

@@ -479,6 +479,13 @@ struct RtContext {
     int wave_blocks1[4] = {RT_WAVE_SHADE_MIN_BLOCKS, RT_WAVE_FINISH_MIN_BLOCKS, RT_WAVE_PREPASS_MIN_BLOCKS,
                            RT_WAVE_WALK_MIN_BLOCKS};  // blocks per SM of shade, finish, pre-pass, walk: one group
     int wave_blocks2[4] = {8, 8, 4, 5};               // ... two groups (measured best: full grids on both streams)
+    // the wave loop as a CUDA graph: a WHILE node whose body is `wave_body_waves` waves of every group
+    bool wave_graph_enabled = true;
+    int wave_body_waves = 4;
+    cudaGraph_t wave_graph = nullptr;
+    cudaGraphExec_t wave_exec = nullptr;
+    std::string wave_graph_key;       // bytes of everything the graph's nodes were built from
+    unsigned long long* d_graph_launches = nullptr;  // kernels the graph bodies have run (device-side count)
     void* wave_staging = nullptr;     // per-sample radiance planes of the current batch
     size_t wave_staging_bytes = 0;
     size_t wave_staging_budget = (size_t)8192 << 20;  // upper bound; clamped to what the device has free
@@ -639,6 +646,103 @@ int wave_reserve(RtContext* ctx, uint32_t slots, int groups, size_t staging_byte
     return RT_OK;
 }
 
+// The wave loop of one batch as a CUDA graph: a WHILE node whose body runs `body_waves` waves of every
+// slot group — one chain of kernels per group, the chains side by side, group g rotated g * lead
+// kernels into its cycle (its first g * lead kernels ran before the loop) so that memory-bound and
+// issue-bound kernels of different groups overlap — and ends with wave_continue_kernel, which keeps
+// the loop going while any slot is live. One graph launch replaces ~1600 kernel launches and every
+// host synchronisation of the loop: rt_render returns at once, and the loop stops within one body
+// of the last path instead of running up to two 8-wave chunks empty.
+int wave_graph_build(RtContext* ctx, const rtw::WaveParams* p, int groups, const unsigned* blocks, bool shallow) {
+    const int body_waves = ctx->wave_body_waves;
+    std::string key;
+    key.append((const char*)p, sizeof(rtw::WaveParams) * (size_t)groups);
+    key.append((const char*)blocks, sizeof(unsigned) * 4);
+    key.push_back((char)groups);
+    key.push_back((char)body_waves);
+    key.push_back(shallow ? 1 : 0);
+    if (ctx->wave_exec && key == ctx->wave_graph_key) return RT_OK;
+    if (ctx->wave_exec) cudaGraphExecDestroy(ctx->wave_exec);
+    if (ctx->wave_graph) cudaGraphDestroy(ctx->wave_graph);
+    ctx->wave_exec = nullptr;
+    ctx->wave_graph = nullptr;
+    ctx->wave_graph_key.clear();
+    if (!ctx->d_graph_launches) {
+        RT_CUDA(ctx, cudaMalloc(&ctx->d_graph_launches, sizeof(unsigned long long)));
+        RT_CUDA(ctx, cudaMemset(ctx->d_graph_launches, 0, sizeof(unsigned long long)));
+    }
+    cudaGraph_t graph = nullptr;
+    RT_CUDA(ctx, cudaGraphCreate(&graph, 0));
+    auto bail = [&](const char* what, cudaError_t e) {
+        cudaGraphDestroy(graph);
+        return fail(ctx, RT_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+    };
+    cudaGraphConditionalHandle handle;
+    cudaError_t e = cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault);
+    if (e != cudaSuccess) return bail("cudaGraphConditionalHandleCreate", e);
+    cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = handle;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t loop;
+    e = cudaGraphAddNode(&loop, graph, nullptr, 0, &np);
+    if (e != cudaSuccess) return bail("cudaGraphAddNode(while)", e);
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+
+    void* const funcs[4] = {(void*)rtw::wave_shade_kernel, (void*)rtw::wave_finish_kernel, (void*)rtw::wave_prepass_kernel,
+                            shallow ? (void*)rtw::wave_walk_kernel<true> : (void*)rtw::wave_walk_kernel<false>};
+    const unsigned threads[4] = {(unsigned)rtw::kShadeThreads, (unsigned)rtw::kFinishThreads, (unsigned)rtw::kPrepassThreads,
+                                 (unsigned)rtw::kWalkThreads};
+    const int lead = 4 / groups > 0 ? 4 / groups : 1;
+    std::vector<cudaGraphNode_t> tails;
+    for (int g = 0; g < groups; g++) {
+        cudaGraphNode_t prev = nullptr;
+        for (int i = 0; i < 4 * body_waves; i++) {
+            const int j = i + g * lead;  // position in the group's own cycle
+            rtw::WaveParams arg = p[g];
+            arg.wave = (uint32_t)(j / 4) & 1u;
+            void* args[1] = {&arg};
+            cudaKernelNodeParams kp;
+            memset(&kp, 0, sizeof kp);
+            kp.func = funcs[j % 4];
+            kp.gridDim = dim3(blocks[j % 4]);
+            kp.blockDim = dim3(threads[j % 4]);
+            kp.kernelParams = args;
+            cudaGraphNode_t node;
+            e = cudaGraphAddKernelNode(&node, body, prev ? &prev : nullptr, prev ? 1 : 0, &kp);
+            if (e != cudaSuccess) return bail("cudaGraphAddKernelNode", e);
+            prev = node;
+        }
+        tails.push_back(prev);
+    }
+    {
+        rtw::WaveLoopCtrl lc;
+        memset(&lc, 0, sizeof lc);
+        for (int g = 0; g < groups; g++) lc.group[g] = p[g].b.ctrl;
+        lc.groups = (uint32_t)groups;
+        lc.body_kernels = (uint32_t)(groups * 4 * body_waves + 1);
+        lc.launches = ctx->d_graph_launches;
+        void* args[2] = {&handle, &lc};
+        cudaKernelNodeParams kp;
+        memset(&kp, 0, sizeof kp);
+        kp.func = (void*)rtw::wave_continue_kernel;
+        kp.gridDim = dim3(1);
+        kp.blockDim = dim3(1);
+        kp.kernelParams = args;
+        cudaGraphNode_t node;
+        e = cudaGraphAddKernelNode(&node, body, tails.data(), tails.size(), &kp);
+        if (e != cudaSuccess) return bail("cudaGraphAddKernelNode(continue)", e);
+    }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess) return bail("cudaGraphInstantiate", e);
+    ctx->wave_graph = graph;
+    ctx->wave_exec = exec;
+    ctx->wave_graph_key = key;
+    return RT_OK;
+}
+
 // Renders the sample range in batches. Inside a batch the paths are independent work items
 // handed to the slots as they free up; waves run until every slot has retired, then the
 // staged samples are added to the accumulation buffer in sample order. The slots form two
@@ -741,6 +845,11 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
         }
     };
 
+    // The loop runs as one CUDA graph unless per-kernel timing was asked for (events around every
+    // launch need the host-paced loop) or RT_WAVE_GRAPH=0.
+    const bool use_graph = ctx->wave_graph_enabled && !timeline && groups <= 4;
+    const unsigned blocks4[4] = {shade_blocks, finish_blocks, prepass_blocks, walk_blocks};
+
     int status = RT_OK;
     cudaEvent_t t_begin = nullptr, t_end = nullptr;
     if (timeline) {
@@ -755,6 +864,40 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
             p[g].path_total = base.pixel_ids * p[g].batch_count;
         }
         cudaMemsetAsync(ctx->wave_next_path, 0, sizeof(uint32_t), ctx->stream);
+        if (use_graph) {
+            // everything on the context's stream: init, the head start of groups 1.., the loop, the sum
+            const int lead = 4 / groups > 0 ? 4 / groups : 1;
+            for (int g = 0; g < groups; g++) {
+                rtw::wave_init_kernel<<<(per_group + 255) / 256, 256, 0, ctx->stream>>>(p[g]);
+                ctx->launches++;
+            }
+            for (int g = 1; g < groups; g++) {
+                p[g].wave = 0u;
+                for (int k = 0; k < g * lead && k < 4; k++) {
+                    if (k == 0) rtw::wave_shade_kernel<<<shade_blocks, rtw::kShadeThreads, 0, ctx->stream>>>(p[g]);
+                    else if (k == 1) rtw::wave_finish_kernel<<<finish_blocks, rtw::kFinishThreads, 0, ctx->stream>>>(p[g]);
+                    else if (k == 2) rtw::wave_prepass_kernel<<<prepass_blocks, rtw::kPrepassThreads, 0, ctx->stream>>>(p[g]);
+                    ctx->launches++;
+                }
+            }
+            cudaError_t ce = cudaGetLastError();
+            if (ce != cudaSuccess) {
+                status = fail(ctx, RT_ERR_CUDA, "wave launch failed: %s", cudaGetErrorString(ce));
+                break;
+            }
+            status = wave_graph_build(ctx, p, groups, blocks4, shallow);
+            if (status != RT_OK) break;
+            ce = cudaGraphLaunch(ctx->wave_exec, ctx->stream);
+            if (ce != cudaSuccess) {
+                status = fail(ctx, RT_ERR_CUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(ce));
+                break;
+            }
+            rtw::wave_accumulate_kernel<<<(unsigned)((pixels + 255) / 256), 256, 0, ctx->stream>>>(p[0]);
+            ctx->launches++;
+            ce = cudaGetLastError();
+            if (ce != cudaSuccess) status = fail(ctx, RT_ERR_CUDA, "accumulate launch failed: %s", cudaGetErrorString(ce));
+            continue;
+        }
         if (groups >= 2) {
             // fork: the group streams start after everything queued on the context's stream
             cudaEventRecord(ctx->wave_fork, ctx->stream);
@@ -1109,6 +1252,11 @@ int rt_create(int device, RtContext** out) {
         long v = atol(k);
         if (v >= 1 && v <= (1l << 18)) ctx->wave_staging_budget = (size_t)v << 20;
     }
+    if (const char* k = getenv("RT_WAVE_GRAPH")) ctx->wave_graph_enabled = atoi(k) != 0;
+    if (const char* k = getenv("RT_WAVE_BODY")) {
+        int v = atoi(k);
+        if (v >= 2 && v <= 32) ctx->wave_body_waves = v & ~1;  // an even number of waves: bodies start on parity 0
+    }
     if (const char* k = getenv("RT_WAVE_GROUPS")) {
         int v = atoi(k);
         ctx->wave_groups = v < 1 ? 1 : (v > RtContext::kMaxGroups ? RtContext::kMaxGroups : v);
@@ -1145,6 +1293,9 @@ void rt_destroy(RtContext* ctx) {
     free_envs(ctx);
     cudaFree(ctx->d_accum_own);
     cudaFree(ctx->d_counters);
+    if (ctx->wave_exec) cudaGraphExecDestroy(ctx->wave_exec);
+    if (ctx->wave_graph) cudaGraphDestroy(ctx->wave_graph);
+    cudaFree(ctx->d_graph_launches);
     cudaFree(ctx->wave_arena);
     cudaFree(ctx->local_arena);
     cudaFree(ctx->d_local_profile);
@@ -1798,7 +1949,16 @@ int rt_timer_stop(RtContext* ctx, float* elapsed_ms) {
     return RT_OK;
 }
 
-uint64_t rt_launch_count(const RtContext* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t rt_launch_count(const RtContext* ctx) {
+    if (!ctx) return 0;
+    unsigned long long in_graphs = 0;  // kernels the wave loop's graph bodies ran: counted on the device
+    if (ctx->d_graph_launches) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(&in_graphs, ctx->d_graph_launches, sizeof in_graphs, cudaMemcpyDeviceToHost);
+    }
+    return ctx->launches + in_graphs;
+}
 
 float rt_first_hit_kernel_ms(const RtContext* ctx) { return ctx ? ctx->first_hit_kernel_ms : 0.f; }
 

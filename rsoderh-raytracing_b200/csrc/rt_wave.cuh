@@ -508,6 +508,21 @@ __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wav
 
 // End of a batch: add the staged sample planes to the accumulation buffer in sample order
 // (shader.wgsl:1367-1371: total += sample, alpha = 1).
+// Last node of the wave loop's graph body (rt_backend.cu, wave_render): the loop goes on while any
+// slot of any group still holds or can get a path.
+struct WaveLoopCtrl {
+    const WaveCtrl* group[4];
+    uint32_t groups;
+    uint32_t body_kernels;              // kernels one body runs, this one included
+    unsigned long long* launches;       // running total, for rt_launch_count
+};
+__global__ void wave_continue_kernel(cudaGraphConditionalHandle handle, const WaveLoopCtrl l) {
+    uint32_t live = 0u;
+    for (uint32_t g = 0; g < l.groups; g++) live += l.group[g]->live;
+    *l.launches += l.body_kernels;
+    cudaGraphSetConditional(handle, live != 0u ? 1u : 0u);
+}
+
 __global__ void wave_accumulate_kernel(const WaveParams p) {
     const size_t pixels = (size_t)p.width * p.height;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
