@@ -887,7 +887,20 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
             }
             status = wave_graph_build(ctx, p, groups, blocks4, shallow);
             if (status != RT_OK) break;
-            ce = cudaGraphLaunch(ctx->wave_exec, ctx->stream);
+            // A caller's stream may be the legacy default stream, on which the graph's two chains
+            // lose their overlap (measured: 4 % slower): the loop then runs on one of the context's
+            // own non-blocking streams, ordered into the caller's stream with a pair of events.
+            cudaStream_t loop_stream = ctx->stream;
+            if (ctx->stream != ctx->own_stream) {
+                loop_stream = ctx->wave_streams[0];
+                ce = cudaEventRecord(ctx->wave_fork, ctx->stream);
+                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(loop_stream, ctx->wave_fork, 0);
+            }
+            if (ce == cudaSuccess) ce = cudaGraphLaunch(ctx->wave_exec, loop_stream);
+            if (ce == cudaSuccess && loop_stream != ctx->stream) {
+                ce = cudaEventRecord(ctx->wave_join[0], loop_stream);
+                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->stream, ctx->wave_join[0], 0);
+            }
             if (ce != cudaSuccess) {
                 status = fail(ctx, RT_ERR_CUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(ce));
                 break;

@@ -211,6 +211,28 @@ def test_white_furnace_energy(rt, orc):
     assert counters["shadow_rays"] > 0 and counters["env_lookups"] > 0
 
 
+@pytest.mark.parametrize("name,w,h,bounces", [("house", 96, 54, 8), ("default", 80, 45, 10), ("suzanne", 64, 36, 8)])
+def test_third_opinion_on_trace_ray(rt, orc, name, w, h, bounces):
+    # oracle/third_opinion.py restates main / trace_ray of shader.wgsl once more (numpy float32
+    # scalars, written from the WGSL, fed by the numpy front-end). 200 random pixel-samples per scene
+    # must equal the C++ oracle's bit for bit: a slip in either transcription would show here.
+    import independent
+    import third_opinion
+    path = os.path.join(ASSETS, "scenes", f"{name}.toml")
+    sky = rt.Environment.synthetic(64, 32)
+    world = third_opinion.World(path, sky.rgb, w, h, bounces)
+    ora = orc.Oracle(independent.IndependentScene(path), independent.IndependentEnvironments([sky.rgb]), w, h,
+                     max_bounces=bounces)
+    rng = np.random.default_rng(2026)
+    values = set()
+    for _ in range(200):
+        x, y, sample = int(rng.integers(0, w)), int(rng.integers(0, h)), int(rng.integers(0, 1 << 20))
+        mine, theirs = world.pixel_sample(x, y, sample), ora.trace_pixel(x, y, sample)
+        assert mine.tobytes() == theirs.tobytes(), (name, x, y, sample, mine, theirs)
+        values.add(mine.tobytes())
+    assert len(values) > 150  # the samples really differ from each other
+
+
 def test_oracle_command_line(rt, orc, tmp_path):
     # oracle/cli.py writes what the parity checks compare; its outputs equal the API's
     import json
