@@ -498,6 +498,7 @@ def main():
                                             else spp for r in range(world)],
                         "msamples_per_s": paths_per_step * steps / (total_ms * 1e-3) / 1e6,
                         "render_ms_rank_max": total_kernel_ms / steps,
+                        "step_ms_rank0": [round(v, 3) for v in step_ms],
                         "reduce_ms": (total_ms - total_kernel_ms) / steps,
                         "algorithmic_work": detail_note}
         if reduce_check is not None:

@@ -13,7 +13,7 @@ port=29500
 for n in 1 2 4 8; do
   [ $n -le $N ] || continue
   for mode in strong weak; do
-    [ $mode = weak ] && [ $n -eq 1 ] && continue
+    [ $mode = weak ] && [ $n -ne ${WEAK_AT:-8} ] && continue
     port=$((port+1))
     out=gpurun_out/bench_r2_${TAG}_B_${mode}_g$n.json
     if [ $n -eq 1 ]; then
