@@ -120,57 +120,113 @@ def algorithmic_ops(c):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs. Every 200 ms: the
-    queries themselves slow the render down (measured on the headline step: 100 ms polling -3 %,
-    1000 ms polling none)."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and the throttle reasons of one GPU while the timed region runs.
 
-    def __init__(self, gpu_index):
+    In-process NVML (pynvml) from a thread: an `nvidia-smi -lms` child was measured to stall the
+    renders of EVERY GPU of the box by 10-16 ms whenever one of its polls landed in a step (both
+    ranks of an N = 2 run slowed down in the same steps; its start-up cost another 12 + 6 + 2 ms
+    over the first three steps). The sampler therefore starts before the warm-up steps, polls every
+    BENCH_SAMPLER_MS (default 500) ms, and only samples taken after mark() — the start of the timed
+    region — are reported. Falls back to one nvidia-smi child if pynvml is unavailable."""
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+               ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+               ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
+    SMI_FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                  "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index, uuid=None):
+        self.interval = max(0.05, float(os.environ.get("BENCH_SAMPLER_MS", "500")) / 1e3)
+        self.samples = []       # (t, sm_mhz, power_w, reason names)
+        self.t_mark = None
+        self.stop_flag = threading.Event()
+        self.sm_max = None
+        self.backend = None
         self.proc = None
-        self.lines = []
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_SAMPLER_MS", "200")],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            if uuid:
+                try:
+                    handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if isinstance(uuid, str) else uuid)
+                except pynvml.NVMLError:
+                    handle = None
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nvml, self.handle = pynvml, handle
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.backend = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
+        except Exception:   # no pynvml / no NVML: one nvidia-smi child
+            try:
+                self.proc = subprocess.Popen(
+                    ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.SMI_FIELDS}",
+                     "--format=csv,noheader,nounits", "-lms", str(int(self.interval * 1e3))],
+                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.backend = "nvidia-smi"
+                self.thread = threading.Thread(target=self._read_smi, daemon=True)
+                self.thread.start()
+            except OSError:
+                self.backend = None
 
-    def _read(self):
+    def _poll_nvml(self):
+        nv, h = self.nvml, self.handle
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                try:
+                    power = nv.nvmlDeviceGetPowerUsage(h) / 1e3
+                except nv.NVMLError:
+                    power = None
+                names = [name for name, const in self.REASONS if mask & getattr(nv, const)]
+                self.samples.append((time.perf_counter(), sm, power, names))
+            except Exception:
+                pass
+            self.stop_flag.wait(self.interval)
+
+    def _read_smi(self):
+        names = [name for name, _ in self.REASONS]
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-                power.append(float(parts[2]))
+                sm, mx, power = float(parts[0]), float(parts[1]), float(parts[2])
             except ValueError:
                 continue
-            for n, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm),
-                "reasons": sorted(reasons)}
+            self.sm_max = mx
+            active = [n for n, v in zip(names, parts[3:7]) if v.lower().startswith("active")]
+            self.samples.append((time.perf_counter(), sm, power, active))
+
+    def mark(self):
+        """Start of the timed region: earlier samples (warm-up) are not reported."""
+        self.t_mark = time.perf_counter()
+
+    def stop(self):
+        if not self.backend:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"]}
+        t_end = time.perf_counter()
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        else:
+            self.thread.join(timeout=2)
+        t0 = self.t_mark if self.t_mark is not None else 0.0
+        inside = [s for s in self.samples if t0 <= s[0] <= t_end] or self.samples[-1:]
+        sm = sorted(s[1] for s in inside)
+        power = [s[2] for s in inside if s[2] is not None]
+        reasons = sorted({n for s in inside for n in s[3]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max,
+                "power_w_max": max(power) if power else None, "samples": len(inside),
+                "reasons": reasons, "source": f"{self.backend}, every {int(self.interval * 1e3)} ms"}
 
 
 # ---- the CPU arm ------------------------------------------------------------------------------
@@ -325,16 +381,29 @@ def main():
         return float(t.item())
 
     steps, warmup = args.steps, max(args.warmup, 3)
+
+    def make_sampler():
+        # rank 0 samples its own GPU; started before the warm-up steps so that its start-up cost
+        # does not land in the timed region
+        if rank != 0:
+            return None
+        try:
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+        except Exception:
+            uuid = None
+        return ClockSampler(local_rank, uuid)
     out = {"metric": "Mrays/s", "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
            "higher_is_better": True, "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
 
     if first_hit:
         # ---- config C: primary rays only. Every rank renders the whole map (replicas). ----
         host_maps = (rt.pinned_array((height, width), np.uint32), rt.pinned_array((height, width), np.float32))
+        sampler = make_sampler()
         for _ in range(warmup):
             state.first_hit(0, out=host_maps)
         barrier()
-        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.mark()
         launches_before = state.launch_count()
         kernel_ms, e2e_ms = [], []
         for _ in range(steps):
@@ -406,12 +475,14 @@ def main():
             host_accum.copy_(accum, non_blocking=True)
             stream.synchronize()
 
+        sampler = make_sampler()
         for _ in range(warmup):
             render_and_reduce()
         barrier()
 
         # ---- timed: device-resident ----
-        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.mark()
         state.reset_counters()
         launches_before = state.launch_count()
         step_ms, kernel_ms = [], []
@@ -433,6 +504,9 @@ def main():
             kernel_ms.append(e0.elapsed_time(e1))
         launches = state.launch_count() - launches_before
         timed = state.counters()   # paths / rays / shadow rays of the timed kernels themselves
+        if os.environ.get("BENCH_DEBUG"):
+            print(f"[bench rank {rank}] step_ms {[round(v, 2) for v in step_ms]} render_ms "
+                  f"{[round(v, 2) for v in kernel_ms]}", file=sys.stderr, flush=True)
         # One more step with per-kernel timing on (rt_set_profiling), kept out of `value`'s steps.
         state.set_profiling(True)
         flush.fill_(1)

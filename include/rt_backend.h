@@ -149,6 +149,20 @@ int rt_get_profile(RtContext* ctx, RtWaveProfile* out);
 int rt_set_memory_budget(RtContext* ctx, uint64_t staging_bytes, uint32_t path_slots);
 int rt_get_memory_usage(RtContext* ctx, uint64_t* bytes);
 
+/* build_bvh (src/bvh.rs:13-28; build_sah :215-337, flatten :155-178) on the device. Produces the
+ * node array and leaf-ordered primitive list of rt_scene_finalize's host builder byte for byte —
+ * same pre-order node indices, same slot order (the reference's sequential swap partition,
+ * bvh.rs:304-315, has a closed form that is evaluated in parallel), same bounds down to the sign
+ * of a zero — one level of the tree per pass (csrc/rt_bvh_build.cuh). rt_bvh_build uploads the
+ * input, builds, and leaves the result on the device; rt_bvh_build_fetch copies it out (either
+ * pointer may be NULL) and releases it. node_count_out <= 2 * primitives - 1. device_ms_out
+ * (optional) is the time of the device work alone, uploads and downloads excluded.
+ * Errors: RT_ERR_SCENE "scene has no primitives" (bvh.rs:222) and "bounds have non-zero surface
+ * area" (a NaN SAH cost, bvh.rs:296), like the host builder. */
+int rt_bvh_build(RtContext* ctx, const RtBvhBuildInput* input, uint32_t* node_count_out,
+                 uint32_t* depth_out, float* device_ms_out);
+int rt_bvh_build_fetch(RtContext* ctx, RtBvhNode* nodes_out, RtPrimitiveInfo* primitives_out);
+
 int rt_set_detailed_counters(RtContext* ctx, int enabled);
 int rt_reset_counters(RtContext* ctx);
 int rt_get_counters(RtContext* ctx, RtCounters* out); /* synchronises */

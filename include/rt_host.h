@@ -55,6 +55,20 @@ int rt_scene_finalize(RtHostScene* s, char* err, size_t err_len);
 int rt_scene_synthetic_field(const char* assets_dir, uint32_t grid, uint32_t seed,
                              RtHostScene** out, char* err, size_t err_len);
 
+/* The same scene with or without its BVH: build_bvh = 0 leaves the node and primitive arrays empty
+ * for a device build (rt_bvh_build, rt_backend.h) that rt_scene_set_bvh then installs. */
+int rt_scene_synthetic_field_ex(const char* assets_dir, uint32_t grid, uint32_t seed, int build_bvh,
+                                RtHostScene** out, char* err, size_t err_len);
+/* Input of build_bvh (src/bvh.rs:13-28) as the device builder takes it: the packed primitive
+ * arrays plus Plane::bounds (scene.rs:203-207) of every plane. Pointers stay valid until
+ * rt_scene_free(). */
+int rt_scene_bvh_input(const RtHostScene* s, RtBvhBuildInput* out);
+/* Installs a BVH built elsewhere (rt_bvh_build): flattened nodes, leaf-ordered primitives, depth. */
+int rt_scene_set_bvh(RtHostScene* s, const RtBvhNode* nodes, uint32_t node_count,
+                     const RtPrimitiveInfo* primitives, uint32_t primitive_count, uint32_t depth);
+/* (Re)builds the BVH with the host builder (what rt_scene_finalize does). */
+int rt_scene_build_bvh(RtHostScene* s, char* err, size_t err_len);
+
 void rt_scene_free(RtHostScene* s);
 
 /* Pointers stay valid until rt_scene_free(). */

@@ -107,6 +107,18 @@ typedef struct RtSceneDesc {
     const RtBvhNode* bvh_nodes;         uint32_t bvh_node_count;
 } RtSceneDesc;
 
+/* Input of build_bvh (src/bvh.rs:13-28): the primitive arrays PrimitiveInfo::build_array walks
+ * (bvh.rs:40-72) — spheres, then planes, then triangles. A baked RtPlane no longer holds the
+ * `forward` / `right` edges its bounds are made of (Plane::bounds, scene.rs:203-207: the box of
+ * `pos` and `pos + forward + right`), so plane boxes come ready made: 6 floats per plane,
+ * min xyz then max xyz (rt_scene_bvh_input fills them). */
+typedef struct RtBvhBuildInput {
+    const RtSphere* spheres;      uint32_t sphere_count;
+    const float* plane_bounds;    uint32_t plane_count;
+    const RtVec3* vertices;       uint32_t vertex_count;
+    const RtTriangle* triangles;  uint32_t triangle_count;
+} RtBvhBuildInput;
+
 /* One environment: the rgba32float texture of src/texture.rs:96-149 (alpha = 0) plus its
  * alias table (src/environments.rs:97-186). alias has width*height entries. */
 typedef struct RtEnvironmentDesc {

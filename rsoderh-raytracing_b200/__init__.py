@@ -5,8 +5,8 @@ is imported under the module name `rsoderh_raytracing_b200` through `_pkg.load()
 the repo root.
 """
 from .api import (REFERENCE_MAX_BOUNCES, Camera, Environment, EnvironmentMaps, RtError, Scene,
-                  SceneBuilder, State, StateGroup, pinned_array, write_pfm, write_png)
+                  DeviceBvhBuilder, SceneBuilder, State, StateGroup, pinned_array, write_pfm, write_png)
 from . import _ffi, samplesplit
 
 __all__ = ["REFERENCE_MAX_BOUNCES", "Camera", "Environment", "EnvironmentMaps", "RtError",
-           "Scene", "SceneBuilder", "State", "StateGroup", "pinned_array", "write_pfm", "write_png", "_ffi", "samplesplit"]
+           "Scene", "DeviceBvhBuilder", "SceneBuilder", "State", "StateGroup", "pinned_array", "write_pfm", "write_png", "_ffi", "samplesplit"]

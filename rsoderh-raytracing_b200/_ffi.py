@@ -83,6 +83,13 @@ class RtSceneDesc(C.Structure):
                 ("bvh_nodes", C.c_void_p), ("bvh_node_count", C.c_uint32)]
 
 
+class RtBvhBuildInput(C.Structure):
+    _fields_ = [("spheres", C.c_void_p), ("sphere_count", C.c_uint32),
+                ("plane_bounds", C.c_void_p), ("plane_count", C.c_uint32),
+                ("vertices", C.c_void_p), ("vertex_count", C.c_uint32),
+                ("triangles", C.c_void_p), ("triangle_count", C.c_uint32)]
+
+
 class RtEnvironmentDesc(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("rgba", C.c_void_p),
                 ("alias", C.c_void_p)]
@@ -117,6 +124,11 @@ HOST_SIGNATURES = {
     "rt_scene_set_camera": (C.c_int, [_vp, _f3, C.c_float, C.c_float, C.c_float]),
     "rt_scene_finalize": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
     "rt_scene_synthetic_field": (C.c_int, [C.c_char_p, _u32, _u32, C.POINTER(_vp), C.c_char_p, C.c_size_t]),
+    "rt_scene_synthetic_field_ex": (C.c_int, [C.c_char_p, _u32, _u32, C.c_int, C.POINTER(_vp), C.c_char_p,
+                                              C.c_size_t]),
+    "rt_scene_bvh_input": (C.c_int, [_vp, C.POINTER(RtBvhBuildInput)]),
+    "rt_scene_set_bvh": (C.c_int, [_vp, _vp, _u32, _vp, _u32, _u32]),
+    "rt_scene_build_bvh": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
     "rt_scene_free": (None, [_vp]),
     "rt_scene_desc": (C.c_int, [_vp, C.POINTER(RtSceneDesc)]),
     "rt_scene_camera": (C.c_int, [_vp, _f3, _f3, _f3, _f3]),
@@ -166,6 +178,9 @@ BACKEND_SIGNATURES = {
     "rt_first_hit": (C.c_int, [_vp, _u32, _vp, _vp]),
     "rt_first_hit_kernel_ms": (C.c_float, [_vp]),
     "rt_debug_view": (C.c_int, [_vp, _u32, _u32, _u32, _vp]),
+    "rt_bvh_build": (C.c_int, [_vp, C.POINTER(RtBvhBuildInput), C.POINTER(_u32), C.POINTER(_u32),
+                               C.POINTER(C.c_float)]),
+    "rt_bvh_build_fetch": (C.c_int, [_vp, _vp, _vp]),
     "rt_set_memory_budget": (C.c_int, [_vp, C.c_uint64, _u32]),
     "rt_get_memory_usage": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "rt_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),

@@ -19,7 +19,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _ffi
-from ._ffi import (RtAliasEntry, RtBvhNode, RtCameraUniform, RtCounters, RtEnvironmentDesc,
+from ._ffi import (RtAliasEntry, RtBvhBuildInput, RtBvhNode, RtCameraUniform, RtCounters, RtEnvironmentDesc,
                    RtMaterial, RtPlane, RtPrimitiveInfo, RtSceneDesc, RtSphere, RtTriangle, RtVec3)
 
 REFERENCE_MAX_BOUNCES = 10  # shader.wgsl:232
@@ -115,14 +115,45 @@ class Scene:
         return Scene(handle)
 
     @staticmethod
-    def synthetic_field(assets_dir: str, grid: int, seed: int = 0x5EED) -> "Scene":
+    def synthetic_field(assets_dir: str, grid: int, seed: int = 0x5EED, build_bvh: bool = True) -> "Scene":
+        """build_bvh=False leaves the BVH to `DeviceBvhBuilder.build(scene)`."""
         handle = C.c_void_p()
         err = _err_buf()
-        st = _ffi.host_lib().rt_scene_synthetic_field(os.fspath(assets_dir).encode(), grid, seed,
-                                                      C.byref(handle), err, len(err))
+        st = _ffi.host_lib().rt_scene_synthetic_field_ex(os.fspath(assets_dir).encode(), grid, seed,
+                                                         1 if build_bvh else 0, C.byref(handle), err, len(err))
         if st:
             raise RtError(st, err.value.decode())
         return Scene(handle)
+
+    def refresh(self):
+        """Re-reads the buffer pointers after the BVH was replaced."""
+        st = _ffi.host_lib().rt_scene_desc(self._handle, C.byref(self._desc))
+        if st:
+            raise RtError(st, "scene is not finalised")
+
+    def bvh_input(self) -> RtBvhBuildInput:
+        """Input of build_bvh as the device builder takes it (rt_scene_bvh_input)."""
+        inp = RtBvhBuildInput()
+        st = _ffi.host_lib().rt_scene_bvh_input(self._handle, C.byref(inp))
+        if st:
+            raise RtError(st, "scene is not finalised")
+        return inp
+
+    def plane_bounds(self) -> np.ndarray:
+        """Plane::bounds (scene.rs:203-207) of every plane: [min xyz, max xyz]."""
+        inp = self.bvh_input()
+        if not inp.plane_count:
+            return np.zeros((0, 6), dtype=np.float32)
+        buf = C.cast(inp.plane_bounds, C.POINTER(C.c_float * (6 * inp.plane_count))).contents
+        return np.frombuffer(buf, dtype=np.float32).reshape(inp.plane_count, 6).copy()
+
+    def build_bvh_host(self):
+        """build_bvh (bvh.rs:13-28) with the host builder (what load_toml does)."""
+        err = _err_buf()
+        st = _ffi.host_lib().rt_scene_build_bvh(self._handle, err, len(err))
+        if st:
+            raise RtError(st, err.value.decode())
+        self.refresh()
 
     @property
     def desc(self) -> RtSceneDesc:
@@ -170,6 +201,55 @@ class Scene:
                 "vertices": d.vertex_count, "normals": d.normal_count,
                 "triangles": d.triangle_count, "primitives": d.primitive_count,
                 "bvh_nodes": d.bvh_node_count}
+
+
+class DeviceBvhBuilder:
+    """build_bvh (bvh.rs:13-28) on the GPU: rt_bvh_build / rt_bvh_build_fetch. The result is
+    byte-identical to the host builder's; `build(scene)` installs it into the scene."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _ffi.backend_lib()
+        self._ctx = C.c_void_p()
+        st = self._lib.rt_create(device, C.byref(self._ctx))
+        if st:
+            raise RtError(st, (self._lib.rt_last_error(None) or b"").decode())
+
+    def close(self):
+        ctx, self._ctx = getattr(self, "_ctx", None), None
+        if ctx:
+            self._lib.rt_destroy(ctx)
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, st: int):
+        if st:
+            raise RtError(st, (self._lib.rt_last_error(self._ctx) or b"").decode())
+
+    def build(self, scene: Scene, install: bool = True) -> dict:
+        import time
+        inp = RtBvhBuildInput()
+        st = _ffi.host_lib().rt_scene_bvh_input(scene._handle, C.byref(inp))
+        if st:
+            raise RtError(st, "scene is not finalised")
+        prims = inp.sphere_count + inp.plane_count + inp.triangle_count
+        node_count, depth, ms = C.c_uint32(), C.c_uint32(), C.c_float()
+        t0 = time.perf_counter()
+        self._check(self._lib.rt_bvh_build(self._ctx, C.byref(inp), C.byref(node_count), C.byref(depth), C.byref(ms)))
+        t1 = time.perf_counter()
+        nodes = np.empty((node_count.value, 12), dtype=np.uint32)
+        primitives = np.empty((prims, 2), dtype=np.uint32)
+        self._check(self._lib.rt_bvh_build_fetch(self._ctx, nodes.ctypes.data, primitives.ctypes.data))
+        t2 = time.perf_counter()
+        if install:
+            st = _ffi.host_lib().rt_scene_set_bvh(scene._handle, nodes.ctypes.data, node_count.value,
+                                                  primitives.ctypes.data, prims, depth.value)
+            if st:
+                raise RtError(st, "rt_scene_set_bvh refused the device-built BVH")
+            scene.refresh()
+        return {"nodes": nodes, "primitives": primitives, "depth": int(depth.value), "device_ms": float(ms.value),
+                "build_call_ms": (t1 - t0) * 1e3, "fetch_ms": (t2 - t1) * 1e3,
+                "install_ms": (time.perf_counter() - t2) * 1e3}
 
 
 class SceneBuilder:

@@ -32,6 +32,7 @@
 #include "rt_fast_host.hpp"
 #include "rt_wave.cuh"
 #include "rt_local.cuh"
+#include "rt_bvh_build.cuh"
 
 using namespace rtd;
 
@@ -412,6 +413,10 @@ std::string g_global_error;
 
 struct RtContext {
     int device = 0;
+    // result of the last rt_bvh_build, until rt_bvh_build_fetch
+    RtBvhNode* d_built_nodes = nullptr;
+    RtPrimitiveInfo* d_built_prims = nullptr;
+    uint32_t built_node_count = 0, built_prim_count = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -485,6 +490,14 @@ struct RtContext {
     cudaGraph_t wave_graph = nullptr;
     cudaGraphExec_t wave_exec = nullptr;
     std::string wave_graph_key;       // bytes of everything the graph's nodes were built from
+    std::string wave_graph_shape;     // what fixes the graph's topology and launch shapes
+    struct WaveGraphNode {
+        cudaGraphNode_t node;
+        int group, kind, wave;        // kernel `kind` of slot group `group`, wave parity `wave`
+    };
+    std::vector<WaveGraphNode> wave_graph_nodes;  // the body's kernel nodes (not wave_continue_kernel)
+    bool wave_graph_update_ok = true;  // cudaGraphExecKernelNodeSetParams works on body nodes (probed once)
+    uint64_t wave_graph_builds = 0, wave_graph_updates = 0;
     unsigned long long* d_graph_launches = nullptr;  // kernels the graph bodies have run (device-side count)
     void* wave_staging = nullptr;     // per-sample radiance planes of the current batch
     size_t wave_staging_bytes = 0;
@@ -662,6 +675,43 @@ int wave_graph_build(RtContext* ctx, const rtw::WaveParams* p, int groups, const
     key.push_back((char)body_waves);
     key.push_back(shallow ? 1 : 0);
     if (ctx->wave_exec && key == ctx->wave_graph_key) return RT_OK;
+    std::string shape;
+    shape.append((const char*)blocks, sizeof(unsigned) * 4);
+    shape.push_back((char)groups);
+    shape.push_back((char)body_waves);
+    shape.push_back(shallow ? 1 : 0);
+    void* const funcs[4] = {(void*)rtw::wave_shade_kernel, (void*)rtw::wave_finish_kernel, (void*)rtw::wave_prepass_kernel,
+                            shallow ? (void*)rtw::wave_walk_kernel<true> : (void*)rtw::wave_walk_kernel<false>};
+    const unsigned threads[4] = {(unsigned)rtw::kShadeThreads, (unsigned)rtw::kFinishThreads, (unsigned)rtw::kPrepassThreads,
+                                 (unsigned)rtw::kWalkThreads};
+    if (ctx->wave_exec && ctx->wave_graph_update_ok && shape == ctx->wave_graph_shape) {
+        // Same topology, new arguments (another scene upload, camera, sample range, buffer): the
+        // instantiated graph keeps its nodes and only their kernel parameters change — a new frame of
+        // an interactive caller costs 64 parameter updates, not a graph instantiation.
+        cudaError_t ue = cudaSuccess;
+        for (const RtContext::WaveGraphNode& n : ctx->wave_graph_nodes) {
+            rtw::WaveParams arg = p[n.group];
+            arg.wave = (uint32_t)n.wave;
+            void* args[1] = {&arg};
+            cudaKernelNodeParams kp;
+            memset(&kp, 0, sizeof kp);
+            kp.func = funcs[n.kind];
+            kp.gridDim = dim3(blocks[n.kind]);
+            kp.blockDim = dim3(threads[n.kind]);
+            kp.kernelParams = args;
+            ue = cudaGraphExecKernelNodeSetParams(ctx->wave_exec, n.node, &kp);
+            if (ue != cudaSuccess) break;
+        }
+        if (ue == cudaSuccess) {
+            ctx->wave_graph_key = key;
+            ctx->wave_graph_updates++;
+            return RT_OK;
+        }
+        cudaGetLastError();                 // not supported for nodes of a conditional body here:
+        ctx->wave_graph_update_ok = false;  // rebuild from now on (some nodes may hold new arguments)
+    }
+    ctx->wave_graph_builds++;
+    ctx->wave_graph_nodes.clear();
     if (ctx->wave_exec) cudaGraphExecDestroy(ctx->wave_exec);
     if (ctx->wave_graph) cudaGraphDestroy(ctx->wave_graph);
     ctx->wave_exec = nullptr;
@@ -690,10 +740,6 @@ int wave_graph_build(RtContext* ctx, const rtw::WaveParams* p, int groups, const
     if (e != cudaSuccess) return bail("cudaGraphAddNode(while)", e);
     cudaGraph_t body = np.conditional.phGraph_out[0];
 
-    void* const funcs[4] = {(void*)rtw::wave_shade_kernel, (void*)rtw::wave_finish_kernel, (void*)rtw::wave_prepass_kernel,
-                            shallow ? (void*)rtw::wave_walk_kernel<true> : (void*)rtw::wave_walk_kernel<false>};
-    const unsigned threads[4] = {(unsigned)rtw::kShadeThreads, (unsigned)rtw::kFinishThreads, (unsigned)rtw::kPrepassThreads,
-                                 (unsigned)rtw::kWalkThreads};
     const int lead = 4 / groups > 0 ? 4 / groups : 1;
     std::vector<cudaGraphNode_t> tails;
     for (int g = 0; g < groups; g++) {
@@ -712,6 +758,7 @@ int wave_graph_build(RtContext* ctx, const rtw::WaveParams* p, int groups, const
             cudaGraphNode_t node;
             e = cudaGraphAddKernelNode(&node, body, prev ? &prev : nullptr, prev ? 1 : 0, &kp);
             if (e != cudaSuccess) return bail("cudaGraphAddKernelNode", e);
+            ctx->wave_graph_nodes.push_back({node, g, j % 4, (j / 4) & 1});
             prev = node;
         }
         tails.push_back(prev);
@@ -740,6 +787,7 @@ int wave_graph_build(RtContext* ctx, const rtw::WaveParams* p, int groups, const
     ctx->wave_graph = graph;
     ctx->wave_exec = exec;
     ctx->wave_graph_key = key;
+    ctx->wave_graph_shape = shape;
     return RT_OK;
 }
 
@@ -1302,6 +1350,10 @@ void rt_destroy(RtContext* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (getenv("RT_WAVE_GRAPH_DEBUG"))
+        fprintf(stderr, "[wave graph] %llu instantiations, %llu parameter updates (node updates %s)\n",
+                (unsigned long long)ctx->wave_graph_builds, (unsigned long long)ctx->wave_graph_updates,
+                ctx->wave_graph_update_ok ? "work" : "refused");
     free_scene(ctx);
     free_envs(ctx);
     cudaFree(ctx->d_accum_own);
@@ -1309,6 +1361,8 @@ void rt_destroy(RtContext* ctx) {
     if (ctx->wave_exec) cudaGraphExecDestroy(ctx->wave_exec);
     if (ctx->wave_graph) cudaGraphDestroy(ctx->wave_graph);
     cudaFree(ctx->d_graph_launches);
+    cudaFree(ctx->d_built_nodes);
+    cudaFree(ctx->d_built_prims);
     cudaFree(ctx->wave_arena);
     cudaFree(ctx->local_arena);
     cudaFree(ctx->d_local_profile);
@@ -1905,6 +1959,230 @@ int rt_get_memory_usage(RtContext* ctx, uint64_t* bytes) {
     *bytes = (uint64_t)ctx->wave_staging_bytes + (uint64_t)ctx->wave_arena_bytes + (uint64_t)ctx->local_arena_bytes +
              (uint64_t)ctx->first_hit_capacity * 8u +
              (ctx->d_accum_own ? (uint64_t)ctx->width * ctx->height * sizeof(float4) : 0u);
+    return RT_OK;
+}
+
+// ---- device BVH build (rt_bvh_build.cuh) ----
+}  // extern "C"
+namespace {
+
+struct ArenaCarver {
+    char* base;
+    size_t used = 0;
+    explicit ArenaCarver(char* b) : base(b) {}
+    template <typename T>
+    T* take(size_t count) {
+        used = (used + 255) & ~(size_t)255;
+        T* p = base ? (T*)(base + used) : nullptr;
+        used += count * sizeof(T);
+        return p;
+    }
+};
+
+// Lays the build's buffers out in one allocation (base == nullptr: only measures).
+size_t bvh_carve(rtb::Build& b, char* base, uint32_t n, uint32_t s, uint32_t pl, uint32_t v, uint32_t t, RtSphere** d_spheres,
+                 float** d_plane_bounds, RtVec3** d_vertices, RtTriangle** d_triangles) {
+    ArenaCarver a(base);
+    b.n = n;
+    b.node_cap = 2u * n;
+    b.acc_cap = n / 6u + 2u;
+    for (int i = 0; i < 2; i++) {
+        b.rmin[i] = a.take<float4>(n);
+        b.rmax[i] = a.take<float4>(n);
+        b.node_of[i] = a.take<uint32_t>(n);
+        b.active[i] = a.take<uint32_t>(b.acc_cap);
+    }
+    b.bucket = a.take<uint8_t>(n);
+    b.prefix = a.take<uint32_t>((size_t)n + 1);
+    b.frpos = a.take<uint32_t>(n);
+    b.bgpos = a.take<uint32_t>(n);
+    b.blocksum = a.take<uint32_t>((size_t)n / rtb::kScanBlock + 4);
+    b.acc = a.take<int>((size_t)rtb::kFields * rtb::kBuckets * b.acc_cap);
+    b.counters = a.take<uint32_t>(4);
+    rtb::Nodes& nd = b.nodes;
+    const size_t c = b.node_cap;
+    nd.begin = a.take<uint32_t>(c);
+    nd.count = a.take<uint32_t>(c);
+    nd.left = a.take<uint32_t>(c);
+    nd.axis = a.take<uint32_t>(c);
+    nd.split = a.take<uint32_t>(c);
+    nd.good = a.take<uint32_t>(c);
+    nd.slot = a.take<uint32_t>(c);
+    nd.bmin = a.take<float4>(c);
+    nd.bmax = a.take<float4>(c);
+    nd.cmin = a.take<float4>(c);
+    nd.cmax = a.take<float4>(c);
+    nd.size = a.take<uint32_t>(c);
+    nd.depth = a.take<uint32_t>(c);
+    nd.pre = a.take<uint32_t>(c);
+    *d_spheres = a.take<RtSphere>(s);
+    *d_plane_bounds = a.take<float>((size_t)pl * 6);
+    *d_vertices = a.take<RtVec3>(v);
+    *d_triangles = a.take<RtTriangle>(t);
+    return a.used + 256;
+}
+
+void bvh_release_result(RtContext* ctx) {
+    cudaFree(ctx->d_built_nodes);
+    cudaFree(ctx->d_built_prims);
+    ctx->d_built_nodes = nullptr;
+    ctx->d_built_prims = nullptr;
+    ctx->built_node_count = ctx->built_prim_count = 0;
+}
+
+}  // namespace
+extern "C" {
+
+int rt_bvh_build(RtContext* ctx, const RtBvhBuildInput* in, uint32_t* node_count_out, uint32_t* depth_out,
+                 float* device_ms_out) {
+    if (!ctx || !in) return RT_ERR_INVALID_ARGUMENT;
+    const uint64_t total = (uint64_t)in->sphere_count + in->plane_count + in->triangle_count;
+    if (total == 0) return fail(ctx, RT_ERR_SCENE, "scene has no primitives");  // bvh.rs:222
+    if (total > 0x3FFFFFFFull) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "too many primitives for a device build");
+    if ((in->sphere_count && !in->spheres) || (in->plane_count && !in->plane_bounds) ||
+        (in->triangle_count && (!in->triangles || !in->vertices)))
+        return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_bvh_build: missing input array");
+    for (uint32_t i = 0; i < in->triangle_count; i++) {
+        const RtTriangle& t = in->triangles[i];
+        if (t.vertex_0 >= in->vertex_count || t.vertex_1 >= in->vertex_count || t.vertex_2 >= in->vertex_count)
+            return fail(ctx, RT_ERR_INVALID_ARGUMENT, "triangle %u names a vertex out of range", i);
+    }
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    bvh_release_result(ctx);
+    const uint32_t n = (uint32_t)total;
+    cudaStream_t st = ctx->stream;
+
+    rtb::Build b;
+    memset(&b, 0, sizeof b);
+    RtSphere* d_spheres = nullptr;
+    float* d_plane_bounds = nullptr;
+    RtVec3* d_vertices = nullptr;
+    RtTriangle* d_triangles = nullptr;
+    const size_t bytes = bvh_carve(b, nullptr, n, in->sphere_count, in->plane_count, in->vertex_count, in->triangle_count,
+                                   &d_spheres, &d_plane_bounds, &d_vertices, &d_triangles);
+    char* arena = nullptr;
+    RT_CUDA(ctx, cudaMalloc(&arena, bytes));
+    bvh_carve(b, arena, n, in->sphere_count, in->plane_count, in->vertex_count, in->triangle_count, &d_spheres,
+              &d_plane_bounds, &d_vertices, &d_triangles);
+    int status = RT_OK;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<uint32_t> level_start;
+    uint32_t host_counters[4] = {0, 0, 0, 0};
+    auto check = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && status == RT_OK)
+            status = fail(ctx, e == cudaErrorMemoryAllocation ? RT_ERR_OUT_OF_MEMORY : RT_ERR_CUDA, "%s failed: %s", what,
+                          cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
+    auto grid = [](size_t items, int threads) { return (unsigned)((items + (size_t)threads - 1) / (size_t)threads); };
+    do {
+        if (in->sphere_count && !check(cudaMemcpyAsync(d_spheres, in->spheres, (size_t)in->sphere_count * sizeof(RtSphere), cudaMemcpyHostToDevice, st), "sphere upload")) break;
+        if (in->plane_count && !check(cudaMemcpyAsync(d_plane_bounds, in->plane_bounds, (size_t)in->plane_count * 6 * sizeof(float), cudaMemcpyHostToDevice, st), "plane upload")) break;
+        if (in->triangle_count) {
+            if (!check(cudaMemcpyAsync(d_vertices, in->vertices, (size_t)in->vertex_count * sizeof(RtVec3), cudaMemcpyHostToDevice, st), "vertex upload")) break;
+            if (!check(cudaMemcpyAsync(d_triangles, in->triangles, (size_t)in->triangle_count * sizeof(RtTriangle), cudaMemcpyHostToDevice, st), "triangle upload")) break;
+        }
+        if (!check(cudaEventCreate(&ev0), "cudaEventCreate") || !check(cudaEventCreate(&ev1), "cudaEventCreate")) break;
+        cudaEventRecord(ev0, st);
+        cudaMemsetAsync(b.counters, 0, 4 * sizeof(uint32_t), st);
+        rtb::init_records_kernel<<<grid(n, rtb::kThreads), rtb::kThreads, 0, st>>>(
+            b, d_spheres, in->sphere_count, d_plane_bounds, in->plane_count, d_vertices, d_triangles,
+            n <= rtb::kLeafMax ? 1u : 0u);
+        rtb::acc_init_kernel<<<grid((size_t)rtb::kFields * rtb::kBuckets, 256), 256, 0, st>>>(b, 1u);
+        rtb::bucket_kernel<true><<<grid(n, rtb::kThreads), rtb::kThreads, 0, st>>>(b, 0);
+        rtb::root_kernel<<<1, 32, 0, st>>>(b);
+        ctx->launches += 4;
+        if (!check(cudaMemcpyAsync(host_counters, b.counters, sizeof host_counters, cudaMemcpyDeviceToHost, st), "counter read")) break;
+        if (!check(cudaStreamSynchronize(st), "bvh root pass")) break;
+        level_start.push_back(0u);
+        level_start.push_back(1u);
+        int cur = 0, act = 0;
+        uint32_t active = host_counters[1];
+        const unsigned scan_blocks = grid((size_t)n + 1, rtb::kScanBlock);
+        while (active > 0u && status == RT_OK) {
+            rtb::acc_init_kernel<<<grid((size_t)rtb::kFields * rtb::kBuckets * active, 256), 256, 0, st>>>(b, active);
+            rtb::bucket_kernel<false><<<grid(n, rtb::kThreads), rtb::kThreads, 0, st>>>(b, cur);
+            cudaMemsetAsync(b.counters + 1, 0, sizeof(uint32_t), st);
+            rtb::split_kernel<<<grid(active, 128), 128, 0, st>>>(b, act, active);
+            rtb::flag_count_kernel<<<scan_blocks, rtb::kThreads, 0, st>>>(b, cur);
+            rtb::blocksum_scan_kernel<<<1, 1024, 0, st>>>(b, scan_blocks);
+            rtb::prefix_kernel<<<scan_blocks, rtb::kThreads, 0, st>>>(b, cur);
+            rtb::scatter_kernel<<<grid(n, rtb::kThreads), rtb::kThreads, 0, st>>>(b, cur);
+            rtb::move_kernel<<<grid(n, rtb::kThreads), rtb::kThreads, 0, st>>>(b, cur);
+            ctx->launches += 8;
+            cur ^= 1;
+            act ^= 1;
+            if (!check(cudaMemcpyAsync(host_counters, b.counters, sizeof host_counters, cudaMemcpyDeviceToHost, st), "counter read")) break;
+            if (!check(cudaStreamSynchronize(st), "bvh level pass")) break;
+            if (host_counters[2] & rtb::kErrNanCost) {
+                status = fail(ctx, RT_ERR_SCENE, "bounds have non-zero surface area");  // NotNan::new(..).expect, bvh.rs:296
+                break;
+            }
+            if (host_counters[2]) {
+                status = fail(ctx, RT_ERR_SCENE, host_counters[2] & rtb::kErrEmptySide ? "BVH partition produced an empty side"
+                                                                                        : "BVH node array overflow");
+                break;
+            }
+            level_start.push_back(host_counters[0]);
+            active = host_counters[1];
+            if (level_start.size() > 4096u) {
+                status = fail(ctx, RT_ERR_STATE, "BVH build did not terminate");
+                break;
+            }
+        }
+        if (status != RT_OK) break;
+        const uint32_t node_count = host_counters[0];
+        if (!check(cudaMalloc(&ctx->d_built_nodes, (size_t)node_count * sizeof(RtBvhNode)), "cudaMalloc(nodes)")) break;
+        if (!check(cudaMalloc(&ctx->d_built_prims, (size_t)n * sizeof(RtPrimitiveInfo)), "cudaMalloc(primitives)")) break;
+        rtb::leaf_bounds_kernel<<<grid(node_count, 128), 128, 0, st>>>(b, cur, node_count);
+        ctx->launches++;
+        const size_t levels = level_start.size() - 1;  // level L holds nodes [level_start[L], level_start[L + 1])
+        for (size_t l = levels; l-- > 0;) {
+            const uint32_t first = level_start[l], last = level_start[l + 1];
+            if (last > first) rtb::up_kernel<<<grid(last - first, 128), 128, 0, st>>>(b, first, last);
+            ctx->launches++;
+        }
+        for (size_t l = 0; l < levels; l++) {
+            const uint32_t first = level_start[l], last = level_start[l + 1];
+            if (last > first) rtb::down_kernel<<<grid(last - first, 128), 128, 0, st>>>(b, first, last);
+            ctx->launches++;
+        }
+        rtb::emit_nodes_kernel<<<grid(node_count, 128), 128, 0, st>>>(b, node_count, ctx->d_built_nodes);
+        rtb::emit_primitives_kernel<<<grid(n, 256), 256, 0, st>>>(b, cur, ctx->d_built_prims);
+        ctx->launches += 2;
+        cudaEventRecord(ev1, st);
+        uint32_t depth = 0;
+        if (!check(cudaMemcpyAsync(&depth, b.nodes.depth, sizeof depth, cudaMemcpyDeviceToHost, st), "depth read")) break;
+        if (!check(cudaStreamSynchronize(st), "bvh finish")) break;
+        if (!check(cudaGetLastError(), "bvh kernels")) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        ctx->built_node_count = node_count;
+        ctx->built_prim_count = n;
+        if (node_count_out) *node_count_out = node_count;
+        if (depth_out) *depth_out = depth;
+        if (device_ms_out) *device_ms_out = ms;
+    } while (false);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    cudaStreamSynchronize(st);
+    cudaFree(arena);
+    if (status != RT_OK) bvh_release_result(ctx);
+    return status;
+}
+
+int rt_bvh_build_fetch(RtContext* ctx, RtBvhNode* nodes_out, RtPrimitiveInfo* primitives_out) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!ctx->d_built_nodes) return fail(ctx, RT_ERR_STATE, "rt_bvh_build_fetch without a built BVH");
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (nodes_out)
+        RT_CUDA(ctx, cudaMemcpyAsync(nodes_out, ctx->d_built_nodes, (size_t)ctx->built_node_count * sizeof(RtBvhNode),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    if (primitives_out)
+        RT_CUDA(ctx, cudaMemcpyAsync(primitives_out, ctx->d_built_prims, (size_t)ctx->built_prim_count * sizeof(RtPrimitiveInfo),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bvh_release_result(ctx);
     return RT_OK;
 }
 

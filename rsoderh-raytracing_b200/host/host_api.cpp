@@ -171,6 +171,51 @@ int rt_scene_synthetic_field(const char* assets_dir, uint32_t grid, uint32_t see
     return RT_OK;
 }
 
+int rt_scene_synthetic_field_ex(const char* assets_dir, uint32_t grid, uint32_t seed, int build_bvh,
+                                RtHostScene** out, char* err, size_t err_len) {
+    if (!assets_dir || !out || grid == 0) return RT_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    RtHostScene* s = new RtHostScene();
+    int st = guarded(err, err_len,
+                     [&] { rt::build_synthetic_field(assets_dir, grid, seed, s->scene, build_bvh != 0); });
+    if (st != RT_OK) {
+        delete s;
+        return st;
+    }
+    *out = s;
+    return RT_OK;
+}
+
+int rt_scene_bvh_input(const RtHostScene* s, RtBvhBuildInput* out) {
+    if (!s || !out) return RT_ERR_INVALID_ARGUMENT;
+    if (!s->scene.finalized) return RT_ERR_STATE;
+    const rt::HostScene& h = s->scene;
+    out->spheres = h.u_spheres.data();          out->sphere_count = (uint32_t)h.u_spheres.size();
+    out->plane_bounds = h.plane_bounds.data();  out->plane_count = (uint32_t)h.u_planes.size();
+    out->vertices = h.u_vertices.data();        out->vertex_count = (uint32_t)h.u_vertices.size();
+    out->triangles = h.u_triangles.data();      out->triangle_count = (uint32_t)h.u_triangles.size();
+    return RT_OK;
+}
+
+int rt_scene_set_bvh(RtHostScene* s, const RtBvhNode* nodes, uint32_t node_count,
+                     const RtPrimitiveInfo* primitives, uint32_t primitive_count, uint32_t depth) {
+    if (!s || !nodes || !primitives || node_count == 0) return RT_ERR_INVALID_ARGUMENT;
+    if (!s->scene.finalized) return RT_ERR_STATE;
+    rt::HostScene& h = s->scene;
+    if ((size_t)primitive_count != h.u_spheres.size() + h.u_planes.size() + h.u_triangles.size())
+        return RT_ERR_INVALID_ARGUMENT;
+    h.u_nodes.assign(nodes, nodes + node_count);
+    h.u_primitives.assign(primitives, primitives + primitive_count);
+    h.bvh_depth = depth;
+    return RT_OK;
+}
+
+int rt_scene_build_bvh(RtHostScene* s, char* err, size_t err_len) {
+    if (!s) return RT_ERR_INVALID_ARGUMENT;
+    if (!s->scene.finalized) return RT_ERR_STATE;
+    return guarded(err, err_len, [&] { rt::build_bvh(s->scene); });
+}
+
 void rt_scene_free(RtHostScene* s) { delete s; }
 
 int rt_scene_desc(const RtHostScene* s, RtSceneDesc* out) {

@@ -102,7 +102,7 @@ RtPlane plane_to_uniform(const Plane& p) {
     return u;
 }
 
-void HostScene::finalize() {
+void HostScene::finalize(bool with_bvh) {
     u_materials.clear(); u_spheres.clear(); u_planes.clear();
     u_vertices.clear(); u_normals.clear(); u_triangles.clear();
 
@@ -133,6 +133,20 @@ void HostScene::finalize() {
                                              t.n[1] + no, t.n[2] + no, t.material_id});
         for (Vec3 v : mesh.vertices) u_vertices.push_back(RtVec3{v.x, v.y, v.z, 0.f});
         for (Vec3 n : mesh.normals) u_normals.push_back(RtVec3{n.x, n.y, n.z, 0.f});
+    }
+
+    plane_bounds.clear();
+    for (const Plane& p : planes) {
+        Bounds3 b = Bounds3::identity().extend(p.pos).extend(p.pos + p.forward + p.right);
+        const float six[6] = {b.min.x, b.min.y, b.min.z, b.max.x, b.max.y, b.max.z};
+        plane_bounds.insert(plane_bounds.end(), six, six + 6);
+    }
+    if (!with_bvh) {
+        u_primitives.clear();
+        u_nodes.clear();
+        bvh_depth = 0;
+        finalized = true;
+        return;
     }
 
     const bool timing = std::getenv("RT_HOST_TIMING") != nullptr;

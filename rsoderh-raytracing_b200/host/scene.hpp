@@ -97,8 +97,10 @@ struct HostScene {
     std::vector<RtPrimitiveInfo> u_primitives;
     std::vector<RtBvhNode> u_nodes;
     uint32_t bvh_depth = 0;
+    std::vector<float> plane_bounds;  // Plane::bounds (scene.rs:203-207), 6 floats per plane: input of a device BVH build
 
-    void finalize();  // pack_meshes + to_uniform + build_bvh
+    // pack_meshes + to_uniform + build_bvh; with_bvh = false leaves the BVH to rt_bvh_build (device)
+    void finalize(bool with_bvh = true);
 };
 
 // Scene::load_toml (src/scene.rs:235-252, 324-441). Throws SceneError with the
@@ -125,7 +127,7 @@ uint32_t alias_build_serial(uint32_t w, uint32_t h, const float* rgb, RtAliasEnt
 
 // Config D generator.
 void build_synthetic_field(const std::string& assets_dir, uint32_t grid, uint32_t seed,
-                           HostScene& out);
+                           HostScene& out, bool with_bvh = true);
 
 std::string read_text_file(const std::string& path);  // throws std::runtime_error(strerror)
 

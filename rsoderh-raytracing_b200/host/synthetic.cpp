@@ -23,7 +23,7 @@ struct Pcg {
 }  // namespace
 
 void build_synthetic_field(const std::string& assets_dir, uint32_t grid, uint32_t seed,
-                           HostScene& out) {
+                           HostScene& out, bool with_bvh) {
     out = HostScene();
     auto mat = [&](float r, float g, float b, float rough, float metal) {
         out.materials.push_back(Material{v3(r, g, b), rough, metal, v3(0, 0, 0)});
@@ -86,7 +86,7 @@ void build_synthetic_field(const std::string& assets_dir, uint32_t grid, uint32_
     out.camera.yaw = 0.f;
     out.camera.pitch = -0.30f;
     out.camera.fov_y = 1.2217305f;  // 70 degrees
-    out.finalize();
+    out.finalize(with_bvh);
 }
 
 }  // namespace rt

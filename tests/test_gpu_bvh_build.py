@@ -1,0 +1,102 @@
+"""rt_bvh_build (csrc/rt_bvh_build.cuh): build_bvh (src/bvh.rs:13-28, 215-337) on the device must
+return the host builder's node array and primitive order byte for byte — which the CPU suite in
+turn pins to the SURVEY goldens and to oracle/scene_oracle.py."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from conftest import ASSETS
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(rt, builder, scene):
+    want_nodes, want_prims, want_depth = scene.bvh_nodes_words(), scene.primitives_words(), scene.bvh_depth
+    out = builder.build(scene, install=False)
+    assert out["primitives"].tobytes() == want_prims.tobytes(), (
+        f"{int((out['primitives'] != want_prims).any(axis=1).sum())} primitive slots differ")
+    assert out["nodes"].shape == want_nodes.shape
+    bad = np.argwhere((out["nodes"] != want_nodes).any(axis=1))
+    assert len(bad) == 0, f"{len(bad)} nodes differ, first {bad[:3].ravel().tolist()}: {out['nodes'][bad[0, 0]]} vs {want_nodes[bad[0, 0]]}"
+    assert out["depth"] == want_depth
+    return out
+
+
+@pytest.fixture(scope="module")
+def builder(rt):
+    b = rt.DeviceBvhBuilder(0)
+    yield b
+    b.close()
+
+
+@pytest.mark.parametrize("name", ["house", "default", "suzanne"])
+def test_device_bvh_equals_host_bvh(rt, builder, name):
+    _check(rt, builder, rt.Scene.load_toml(os.path.join(ASSETS, "scenes", f"{name}.toml")))
+
+
+@pytest.mark.parametrize("grid", [1, 2, 7, 20])
+def test_device_bvh_equals_host_bvh_field(rt, builder, grid):
+    _check(rt, builder, rt.Scene.synthetic_field(ASSETS, grid))
+
+
+def test_device_bvh_signed_zeros_degenerate_leaves_small_inputs(rt, builder):
+    rng = np.random.default_rng(3)
+    b = rt.SceneBuilder()
+    b.add_material((0.8, 0.8, 0.8), 1.0, 0.0)
+    for _ in range(9):   # one centroid, nine spheres: a leaf of nine (bvh.rs:238-244)
+        b.add_sphere((1.0, 2.0, 3.0), float(rng.uniform(0.1, 0.4)), 0)
+    for i in range(40):
+        z = 0.0 if i % 3 else -0.0
+        b.add_sphere((float(rng.uniform(-4, 4)), z, float(rng.uniform(-4, 4))), 0.0 if i % 2 else 0.25, 0)
+    verts = np.array([[-0.0, 0.0, 0.0], [1.0, -0.0, 0.0], [0.0, 1.0, -0.0], [0.0, -0.0, 1.0],
+                      [-1.0, 0.0, -0.0], [0.0, -1.0, 0.0]], np.float32)
+    tris = np.array([[0, 1, 2, 0, 0, 0], [0, 2, 3, 0, 0, 0], [0, 3, 4, 0, 0, 0], [0, 4, 5, 0, 0, 0],
+                     [1, 2, 3, 0, 0, 0], [2, 3, 4, 0, 0, 0], [3, 4, 5, 0, 0, 0]], np.uint32)
+    b.add_mesh_raw(verts, np.array([[0, 1, 0]], np.float32), tris, 0)
+    b.add_plane((-0.0, 0.0, -0.0), (0, 0, 5), (5, 0, 0), 0)
+    _check(rt, builder, b.build())
+    for count in (1, 5, 6, 300):
+        s = rt.SceneBuilder()
+        s.add_material((0.8, 0.8, 0.8), 1.0, 0.0)
+        for i in range(count):
+            s.add_sphere((float(rng.uniform(-9, 9)), float(rng.uniform(-9, 9)), float(rng.uniform(-9, 9))), 0.3, 0)
+        _check(rt, builder, s.build())
+
+
+def test_device_bvh_random_soups(rt, builder):
+    """Random triangle soups with many exact ties (snapped coordinates) across sizes that cross the
+    block and scan-tile boundaries of the kernels."""
+    rng = np.random.default_rng(11)
+    for count in (255, 256, 257, 1023, 1024, 1025, 5000, 70001):
+        s = rt.SceneBuilder()
+        s.add_material((0.8, 0.8, 0.8), 1.0, 0.0)
+        v = np.round(rng.uniform(-8, 8, size=(count * 3, 3)) * 4) / 4     # quarter-unit lattice: ties, zeros
+        v = v.astype(np.float32)
+        v[rng.random(len(v)) < 0.02, 1] = -0.0
+        t = np.zeros((count, 6), np.uint32)
+        t[:, 0:3] = np.arange(count * 3, dtype=np.uint32).reshape(count, 3)
+        s.add_mesh_raw(v, np.array([[0, 1, 0]], np.float32), t, 0)
+        _check(rt, builder, s.build())
+
+
+def test_device_bvh_ten_million_triangles_under_half_a_second(rt, builder):
+    """BASELINE.json configs[3]'s scene: same tree as the host builder, built in <= 0.5 s including
+    the upload of the primitive arrays and the download of nodes and primitives."""
+    scene = rt.Scene.synthetic_field(ASSETS, 99)
+    assert scene.counts()["triangles"] == 9997020
+    builder.build(rt.Scene.synthetic_field(ASSETS, 3), install=False)   # warm the context
+    t0 = time.perf_counter()
+    out = _check(rt, builder, scene)
+    _ = time.perf_counter() - t0
+    total_ms = out["build_call_ms"] + out["fetch_ms"]
+    print(f"device BVH build, 9 997 021 primitives: device {out['device_ms']:.1f} ms, call {out['build_call_ms']:.1f} ms, "
+          f"fetch {out['fetch_ms']:.1f} ms, {len(out['nodes'])} nodes, depth {out['depth']}")
+    assert total_ms <= 500.0, f"device build took {total_ms:.0f} ms"
+    # installed, the scene renders like the host-built one (same bytes, so only a smoke check)
+    fresh = rt.Scene.synthetic_field(ASSETS, 3, build_bvh=False)
+    assert fresh.counts()["bvh_nodes"] == 0
+    built = builder.build(fresh)
+    assert fresh.counts()["bvh_nodes"] == len(built["nodes"]) and fresh.bvh_depth == built["depth"]
+    assert fresh.bvh_nodes_words().tobytes() == rt.Scene.synthetic_field(ASSETS, 3).bvh_nodes_words().tobytes()
