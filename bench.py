@@ -98,9 +98,23 @@ def resolve_config(args):
     return cfg
 
 
-def load_scene(rt, cfg):
+def load_scene(rt, cfg, bvh_device=None, info=None):
+    """bvh_device: CUDA device ordinal for the BVH of a generated scene (rt_bvh_build, byte-identical
+    to the host builder); None builds it on the host like Scene::load_toml does."""
     if cfg["scene"].startswith("synthetic:"):
-        return rt.Scene.synthetic_field(os.path.join(ROOT, "assets"), int(cfg["scene"].split(":")[1]))
+        grid = int(cfg["scene"].split(":")[1])
+        if bvh_device is None:
+            return rt.Scene.synthetic_field(os.path.join(ROOT, "assets"), grid)
+        scene = rt.Scene.synthetic_field(os.path.join(ROOT, "assets"), grid, build_bvh=False)
+        builder = rt.DeviceBvhBuilder(bvh_device)
+        t0 = time.perf_counter()
+        built = builder.build(scene)
+        if info is not None:
+            info.update({"where": f"cuda:{bvh_device} (rt_bvh_build)", "device_ms": built["device_ms"],
+                         "with_upload_download_ms": (time.perf_counter() - t0) * 1e3,
+                         "nodes": int(len(built["nodes"])), "depth": built["depth"]})
+        builder.close()
+        return scene
     return rt.Scene.load_toml(os.path.join(ROOT, "assets", "scenes", f"{cfg['scene']}.toml"))
 
 
@@ -356,7 +370,8 @@ def main():
     pixels = width * height
     first_hit = cfg["mode"] == "first_hit"
     t_build = time.perf_counter()
-    scene = load_scene(rt, cfg)
+    bvh_info = {}
+    scene = load_scene(rt, cfg, bvh_device=local_rank, info=bvh_info)
     build_s = time.perf_counter() - t_build
     env = rt.EnvironmentMaps([rt.Environment.synthetic(2048, 1024)])
     state = rt.State(scene, env, width, height, device=local_rank, max_bounces=BOUNCES)
@@ -610,7 +625,15 @@ def main():
                "algorithmic_bytes_per_step": int(abytes), "render_ms": render_s * 1e3}
         measured = load_measured_profile(cfg["name"])
         if measured:
-            issue["measured"] = measured.get("issue")
+            m = dict(measured.get("issue") or {})
+            if m.get("warp_instructions_per_step") and cfg["spp"] == CONFIGS[cfg["name"]]["spp"] and world == 1:
+                # ncu-counted instructions of the same step (profiles/measured.json): how busy the issue
+                # ports were over the timed render, and how much of what they issued was algorithmic work
+                warp_peak = SM_COUNT * 4 * sm_mhz * 1e6      # one warp instruction per scheduler and clock
+                m["issue_slots_used_frac"] = m["warp_instructions_per_step"] / render_s / warp_peak
+                m["algorithmic_share_of_thread_instructions"] = ops / m["thread_instructions_per_step"]
+                m["active_threads_per_instruction"] = m["thread_instructions_per_step"] / m["warp_instructions_per_step"]
+            issue["measured"] = m
             hbm["traffic"] = measured.get("dram_bytes_per_step")
             issue["traffic"] = measured.get("dram_bytes_per_step")
             hbm["traffic_source"] = issue["traffic_source"] = measured.get("source")
@@ -619,7 +642,8 @@ def main():
             "ms_per_step": total_ms / steps, "scaling": scaling,
             "config": dict({"workload": cfg["workload"], "config": cfg["name"],
                             "l2": "256 MiB flush write between timed steps",
-                            "rays_per_step": int(rays_per_step), "scene_build_s": build_s}, **extra_config),
+                            "rays_per_step": int(rays_per_step), "scene_build_s": build_s,
+                            **({"bvh_build": bvh_info} if bvh_info else {})}, **extra_config),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": hbm if cfg["name"] == "D" else issue,
             "roofline_other": issue if cfg["name"] == "D" else hbm,

@@ -80,10 +80,12 @@ int rt_clear(RtContext* ctx);
  * sample_count - 1 (these values seed the per-pixel RNG, shader.wgsl:1309-1312).
  * Accumulates into the accumulation buffer exactly like shader.wgsl:1367-1371.
  * max_bounces is the reference's MAX_BOUNCES (10, shader.wgsl:232) made a parameter.
- * Work is enqueued on the context's stream and ordered with everything else on it. The
- * call paces the wavefront pipeline from the host (it reads a live-path counter one chunk
- * of waves behind the launches), so it returns when the last waves have been queued —
- * close to completion; use rt_sync / rt_read_accum to wait for the result. */
+ * Asynchronous: the work is enqueued on the context's stream, ordered with everything else
+ * on it, and the call returns at once — the wave loop of the render is one CUDA-graph launch
+ * (a WHILE node that runs until every path slot has retired). Use rt_sync / rt_read_accum to
+ * wait for the result. A render makes no call into the kernel-mode driver unless its buffers
+ * have to grow. (With rt_set_profiling on, or RT_WAVE_GRAPH=0, the loop is paced from the
+ * calling thread instead and the call returns when the last waves have been queued.) */
 int rt_render(RtContext* ctx, uint32_t sample_begin, uint32_t sample_count, uint32_t max_bounces,
               uint32_t environment_index);
 

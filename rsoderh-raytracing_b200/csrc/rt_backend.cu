@@ -422,7 +422,12 @@ struct RtContext {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     std::string error;
 
-    // scene
+    // scene: every array below lives in one of two arenas. An upload fills the arena that is not in
+    // use and the two swap on success, so re-uploading a scene of the same size allocates nothing
+    // (no kernel-mode driver call on the per-frame path) and a failed upload leaves the old scene.
+    void* scene_arena[2] = {nullptr, nullptr};
+    size_t scene_arena_bytes[2] = {0, 0};
+    int scene_arena_cur = 0;
     float4* d_nodes = nullptr;
     float4* d_records = nullptr;
     float4* d_tri_normals = nullptr;
@@ -496,6 +501,8 @@ struct RtContext {
         int group, kind, wave;        // kernel `kind` of slot group `group`, wave parity `wave`
     };
     std::vector<WaveGraphNode> wave_graph_nodes;  // the body's kernel nodes (not wave_continue_kernel)
+    cudaGraphNode_t wave_graph_continue = nullptr;   // the body's last node: wave_continue_kernel
+    cudaGraphConditionalHandle wave_graph_handle = 0;
     bool wave_graph_update_ok = true;  // cudaGraphExecKernelNodeSetParams works on body nodes (probed once)
     uint64_t wave_graph_builds = 0, wave_graph_updates = 0;
     unsigned long long* d_graph_launches = nullptr;  // kernels the graph bodies have run (device-side count)
@@ -542,18 +549,12 @@ int fail(RtContext* ctx, int status, const char* fmt, ...) {
     } while (0)
 
 void free_scene(RtContext* ctx) {
-    cudaFree(ctx->d_nodes);
-    cudaFree(ctx->d_records);
-    cudaFree(ctx->d_tri_normals);
-    cudaFree(ctx->d_materials);
-    cudaFree(ctx->d_n2);
-    cudaFree(ctx->d_tri);
-    cudaFree(ctx->d_ana);
-    cudaFree(ctx->d_pre);
-    cudaFree(ctx->d_flat);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(ctx->scene_arena[i]);
+        ctx->scene_arena[i] = nullptr;
+        ctx->scene_arena_bytes[i] = 0;
+    }
     ctx->d_flat = nullptr;
-    cudaFree(ctx->d_big_len);
-    cudaFree(ctx->d_ana_paths);
     ctx->d_ana_paths = nullptr;
     ctx->d_n2 = ctx->d_tri = ctx->d_ana = ctx->d_pre = nullptr;
     ctx->d_big_len = nullptr;
@@ -703,6 +704,23 @@ int wave_graph_build(RtContext* ctx, const rtw::WaveParams* p, int groups, const
             if (ue != cudaSuccess) break;
         }
         if (ue == cudaSuccess) {
+            // the loop condition reads the groups' control blocks, which move with the slot arena
+            rtw::WaveLoopCtrl lc;
+            memset(&lc, 0, sizeof lc);
+            for (int g = 0; g < groups; g++) lc.group[g] = p[g].b.ctrl;
+            lc.groups = (uint32_t)groups;
+            lc.body_kernels = (uint32_t)(groups * 4 * body_waves + 1);
+            lc.launches = ctx->d_graph_launches;
+            void* args[2] = {&ctx->wave_graph_handle, &lc};
+            cudaKernelNodeParams kp;
+            memset(&kp, 0, sizeof kp);
+            kp.func = (void*)rtw::wave_continue_kernel;
+            kp.gridDim = dim3(1);
+            kp.blockDim = dim3(1);
+            kp.kernelParams = args;
+            ue = cudaGraphExecKernelNodeSetParams(ctx->wave_exec, ctx->wave_graph_continue, &kp);
+        }
+        if (ue == cudaSuccess) {
             ctx->wave_graph_key = key;
             ctx->wave_graph_updates++;
             return RT_OK;
@@ -780,6 +798,8 @@ int wave_graph_build(RtContext* ctx, const rtw::WaveParams* p, int groups, const
         cudaGraphNode_t node;
         e = cudaGraphAddKernelNode(&node, body, tails.data(), tails.size(), &kp);
         if (e != cudaSuccess) return bail("cudaGraphAddKernelNode(continue)", e);
+        ctx->wave_graph_continue = node;
+        ctx->wave_graph_handle = handle;
     }
     cudaGraphExec_t exec = nullptr;
     e = cudaGraphInstantiate(&exec, graph, 0);
@@ -819,13 +839,23 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
     const size_t pixels = (size_t)ctx->width * ctx->height;
     // The staging planes must fit what the device has left (the budget is only an upper bound).
     size_t budget = ctx->wave_staging_budget;
+    // Asked only when the planes have to grow: cudaMemGetInfo goes through the kernel-mode driver,
+    // and on a host whose other GPUs are busy that call was measured to block for 2 - 75 ms now and
+    // then (tools/variance_probe.py) — inside what would otherwise be a purely user-mode enqueue.
     {
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            const size_t usable = free_b + ctx->wave_staging_bytes;  // our own planes are reusable
-            const size_t reserve = (size_t)2048 << 20;               // slot arena + headroom for the caller
-            const size_t cap = usable > reserve ? (usable - reserve) / 4 * 3 : usable / 2;
-            if (budget > cap) budget = cap;
+        uint64_t want = sample_count < 1u ? 1u : sample_count;
+        if (want * pixels * sizeof(float4) > budget) want = budget / (pixels * sizeof(float4));
+        if (want < 1u) want = 1u;
+        if (want * pixels * sizeof(float4) <= ctx->wave_staging_bytes) {
+            budget = ctx->wave_staging_bytes;  // what is allocated already holds the batch
+        } else {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                const size_t usable = free_b + ctx->wave_staging_bytes;  // our own planes are reusable
+                const size_t reserve = (size_t)2048 << 20;               // slot arena + headroom for the caller
+                const size_t cap = usable > reserve ? (usable - reserve) / 4 * 3 : usable / 2;
+                if (budget > cap) budget = cap;
+            }
         }
     }
     uint64_t batch = budget / (pixels * sizeof(float4));
@@ -1487,61 +1517,75 @@ int rt_upload_scene(RtContext* ctx, const RtSceneDesc* s) {
     rtf::FastLayout fl;
     rtf::build_fast_layout(*s, fl);
 
-    // ---- upload: into fresh buffers; the scene in use is replaced only when all of it is there ----
-    struct Pending {
-        std::vector<void*> owned;
-        ~Pending() {
-            for (void* q : owned) cudaFree(q);
-        }
-    } pending;
+    // ---- upload: into the arena that is not in use; the scene in use is replaced only when all of
+    // the new one is there ----
+    struct Piece {
+        const void* src;
+        size_t bytes, alloc;
+        size_t offset;
+    };
+    std::vector<Piece> pieces;
+    size_t arena_need = 0;
+    auto piece = [&](const void* src, size_t bytes, size_t alloc_bytes) -> size_t {
+        arena_need = (arena_need + 255) & ~(size_t)255;
+        pieces.push_back({src, bytes, alloc_bytes ? alloc_bytes : 16, arena_need});
+        arena_need += alloc_bytes ? alloc_bytes : 16;
+        return pieces.size() - 1;
+    };
+    auto piece4 = [&](const std::vector<float4>& v, size_t extra = 0) {
+        return piece(v.data(), v.size() * sizeof(float4), (v.size() + extra) * sizeof(float4));
+    };
+    const size_t i_nodes = piece4(nodes), i_records = piece4(records), i_tri_normals = piece4(tri_normals);
+    const size_t i_materials = piece(nullptr, 0, (size_t)s->material_count * 3 * sizeof(float4));
+    const size_t i_raw_materials = piece(s->materials, (size_t)s->material_count * sizeof(RtMaterial),
+                                         (size_t)s->material_count * sizeof(RtMaterial));
+    const size_t i_n2 = piece4(fl.n2), i_tri = piece4(fl.tri, 1), i_ana = piece4(fl.ana), i_pre = piece4(fl.pre),
+                 i_flat = piece4(fl.flat);
+    const size_t i_big_len = fl.big_len.empty() ? (size_t)-1
+                                                : piece(fl.big_len.data(), fl.big_len.size() * sizeof(uint32_t),
+                                                        fl.big_len.size() * sizeof(uint32_t));
+    const size_t i_ana_paths = piece(fl.ana_paths.data(), fl.ana_paths.size() * sizeof(uint32_t),
+                                     fl.ana_paths.size() * sizeof(uint32_t));
+    arena_need += 256;
+    const int spare = ctx->has_scene ? ctx->scene_arena_cur ^ 1 : ctx->scene_arena_cur;
     cudaError_t up_err = cudaSuccess;
-    auto upload = [&](const void* src, size_t bytes, size_t alloc_bytes) -> void* {
-        if (up_err != cudaSuccess) return nullptr;
-        void* d = nullptr;
-        up_err = cudaMalloc(&d, alloc_bytes ? alloc_bytes : 16);
-        if (up_err != cudaSuccess) return nullptr;
-        pending.owned.push_back(d);
-        if (bytes) up_err = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
-        return d;
-    };
-    auto up4 = [&](const std::vector<float4>& v, size_t extra = 0) {
-        return (float4*)upload(v.data(), v.size() * sizeof(float4), (v.size() + extra) * sizeof(float4));
-    };
-    float4* n_nodes = up4(nodes);
-    float4* n_records = up4(records);
-    float4* n_tri_normals = up4(tri_normals);
-    float4* n_materials = (float4*)upload(nullptr, 0, (size_t)s->material_count * 3 * sizeof(float4));
-    float* d_raw_materials = (float*)upload(s->materials, (size_t)s->material_count * sizeof(RtMaterial),
-                                            (size_t)s->material_count * sizeof(RtMaterial));
-    float4* n_n2 = up4(fl.n2);
-    float4* n_tri = up4(fl.tri, 1);
-    float4* n_ana = up4(fl.ana);
-    float4* n_pre = up4(fl.pre);
-    float4* n_flat = up4(fl.flat);
-    uint32_t* n_big_len = fl.big_len.empty() ? nullptr
-                                             : (uint32_t*)upload(fl.big_len.data(), fl.big_len.size() * sizeof(uint32_t),
-                                                                 fl.big_len.size() * sizeof(uint32_t));
-    uint32_t* n_ana_paths = (uint32_t*)upload(fl.ana_paths.data(), fl.ana_paths.size() * sizeof(uint32_t),
-                                              fl.ana_paths.size() * sizeof(uint32_t));
+    if (ctx->scene_arena_bytes[spare] < arena_need) {
+        // the spare arena is not referenced by any queued work: renders use the current one
+        cudaFree(ctx->scene_arena[spare]);
+        ctx->scene_arena[spare] = nullptr;
+        ctx->scene_arena_bytes[spare] = 0;
+        up_err = cudaMalloc(&ctx->scene_arena[spare], arena_need);
+        if (up_err == cudaSuccess) ctx->scene_arena_bytes[spare] = arena_need;
+    }
+    char* arena = (char*)ctx->scene_arena[spare];
+    auto at = [&](size_t i) -> void* { return i == (size_t)-1 ? nullptr : (void*)(arena + pieces[i].offset); };
+    for (size_t i = 0; i < pieces.size() && up_err == cudaSuccess; i++)
+        if (pieces[i].bytes)
+            up_err = cudaMemcpyAsync(at(i), pieces[i].src, pieces[i].bytes, cudaMemcpyHostToDevice, ctx->stream);
+    float4* n_nodes = (float4*)at(i_nodes);
+    float4* n_records = (float4*)at(i_records);
+    float4* n_tri_normals = (float4*)at(i_tri_normals);
+    float4* n_materials = (float4*)at(i_materials);
+    float4* n_n2 = (float4*)at(i_n2);
+    float4* n_tri = (float4*)at(i_tri);
+    float4* n_ana = (float4*)at(i_ana);
+    float4* n_pre = (float4*)at(i_pre);
+    float4* n_flat = (float4*)at(i_flat);
+    uint32_t* n_big_len = (uint32_t*)at(i_big_len);
+    uint32_t* n_ana_paths = (uint32_t*)at(i_ana_paths);
     if (up_err == cudaSuccess) {
         bake_materials_kernel<<<(s->material_count + 127) / 128, 128, 0, ctx->stream>>>(
-            d_raw_materials, n_materials, s->material_count);
+            (const float*)at(i_raw_materials), n_materials, s->material_count);
         ctx->launches++;
         up_err = cudaGetLastError();
     }
-    // also waits for the renders still using the old scene
+    // The host vectors above are pageable: the copies have left them when the calls return, but the
+    // stream is drained anyway so that a failure surfaces here, with the old scene still in place.
     if (up_err == cudaSuccess) up_err = cudaStreamSynchronize(ctx->stream);
     if (up_err != cudaSuccess)
         return fail(ctx, up_err == cudaErrorMemoryAllocation ? RT_ERR_OUT_OF_MEMORY : RT_ERR_CUDA,
                     "scene upload failed: %s (the previous scene is still in place)", cudaGetErrorString(up_err));
-
-    free_scene(ctx);
-    for (void*& q : pending.owned)
-        if (q == (void*)d_raw_materials) {
-            cudaFree(q);
-            q = nullptr;
-        }
-    pending.owned.clear();  // the context owns the rest now
+    ctx->scene_arena_cur = spare;
     ctx->d_nodes = n_nodes;
     ctx->d_records = n_records;
     ctx->d_tri_normals = n_tri_normals;

@@ -39,8 +39,9 @@ if os.environ.get("QB_FIRST_HIT"):
           f"{dt * 1e3:.3f} ms per call incl. 2 D2H copies, hit fraction {(slots != 0xFFFFFFFF).mean():.3f}, "
           f"{scene.counts()['triangles']} triangles, depth {scene.bvh_depth}, scene build {build_s:.2f} s")
     sys.exit(0)
-st.render_samples(2)  # warm-up
-st.sync()
+if not os.environ.get("QB_NO_WARMUP"):   # (ncu whole-step passes count every launch of ONE render)
+    st.render_samples(2)  # warm-up
+    st.sync()
 best = 1e30
 for _ in range(reps):
     st.reset()
