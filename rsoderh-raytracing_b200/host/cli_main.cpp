@@ -5,7 +5,7 @@
 // camera), --movement-keys / --other-keys (accepted and validated with the reference's
 // messages and exit code 2; they have no effect without a window).
 // Added for headless use: --width --height --spp --bounces --env --hdri --out --pfm
-// --first-hit-out --gpus --sample-begin.
+// --first-hit-out --gpus --sample-begin --bvh.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -24,6 +24,7 @@ struct Args {
     std::vector<std::string> scenes, hdris;
     uint32_t width = 1280, height = 720, spp = 64, bounces = 10, env = 0, sample_begin = 0;
     int gpus = 1;
+    std::string bvh = "host";  // "device": rebuild the BVH with rt_bvh_build (same bytes, for large scenes)
 };
 
 [[noreturn]] void usage(const char* msg) {
@@ -32,7 +33,7 @@ struct Args {
                  "Usage: rt_render --scene <SCENE> [--scene <SCENE> ...] [--state <BASE64>]\n"
                  "                 [--width W] [--height H] [--spp N] [--bounces N] [--env I]\n"
                  "                 [--hdri file.hdr ...] [--out image.png] [--pfm image.pfm]\n"
-                 "                 [--first-hit-out slots.u32] [--gpus N] [--sample-begin S]\n"
+                 "                 [--first-hit-out slots.u32] [--gpus N] [--sample-begin S] [--bvh host|device]\n"
                  "                 [--movement-keys wasdqe] [--other-keys cpe]\n");
     std::exit(2);
 }
@@ -74,6 +75,7 @@ int main(int argc, char** argv) {
         else if (take(argc, argv, i, "--env", v)) a.env = (uint32_t)std::strtoul(v.c_str(), nullptr, 10);
         else if (take(argc, argv, i, "--sample-begin", v)) a.sample_begin = (uint32_t)std::strtoul(v.c_str(), nullptr, 10);
         else if (take(argc, argv, i, "--gpus", v)) a.gpus = std::atoi(v.c_str());
+        else if (take(argc, argv, i, "--bvh", v)) a.bvh = v;
         else if (take(argc, argv, i, "--hdri", v)) a.hdris.push_back(v);
         else if (take(argc, argv, i, "--out", v)) a.out = v;
         else if (take(argc, argv, i, "--pfm", v)) a.pfm = v;
@@ -95,6 +97,7 @@ int main(int argc, char** argv) {
         return 2;
     }
     if (!a.width || !a.height || !a.spp || a.gpus < 1) usage("width, height, spp and gpus must be positive");
+    if (a.bvh != "host" && a.bvh != "device") usage("--bvh takes 'host' or 'device'");
 
     char err[1024] = {0};
     RtHostScene* scene = nullptr;
@@ -145,6 +148,25 @@ int main(int argc, char** argv) {
     std::vector<RtEnvironmentDesc> env_descs;
     for (auto& e : envs) env_descs.push_back(RtEnvironmentDesc{e.w, e.h, e.rgba.data(), e.alias.data()});
 
+    if (a.bvh == "device") {
+        // build_bvh (bvh.rs:13-28) on GPU 0: the same node array and slot order as the host builder's
+        RtContext* builder = nullptr;
+        if (rt_create(0, &builder) != RT_OK) return die("GPU setup failed", rt_last_error(nullptr));
+        RtBvhBuildInput input;
+        uint32_t node_count = 0, depth = 0;
+        float device_ms = 0.f;
+        rt_scene_bvh_input(scene, &input);
+        if (rt_bvh_build(builder, &input, &node_count, &depth, &device_ms) != RT_OK)
+            return die("device BVH build failed", rt_last_error(builder));
+        const uint32_t prims = input.sphere_count + input.plane_count + input.triangle_count;
+        std::vector<RtBvhNode> nodes(node_count);
+        std::vector<RtPrimitiveInfo> primitives(prims);
+        if (rt_bvh_build_fetch(builder, nodes.data(), primitives.data()) != RT_OK ||
+            rt_scene_set_bvh(scene, nodes.data(), node_count, primitives.data(), prims, depth) != RT_OK)
+            return die("device BVH build failed", rt_last_error(builder));
+        std::fprintf(stderr, "BVH built on the device in %.2f ms\n", device_ms);
+        rt_destroy(builder);
+    }
     RtSceneDesc desc;
     rt_scene_desc(scene, &desc);
     std::fprintf(stderr, "tree depth: %u\ntree node count: %u\n", rt_scene_bvh_depth(scene),

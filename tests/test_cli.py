@@ -77,3 +77,18 @@ def test_render_to_files_equals_the_python_api(rt, tmp_path):
     slots, _t = st.first_hit(0)
     assert np.array_equal(np.fromfile(hits, dtype=np.uint32).reshape(h, w), slots)
     assert open(png, "rb").read(8) == b"\x89PNG\r\n\x1a\n"
+
+
+@pytest.mark.gpu
+def test_device_built_bvh_renders_the_same_file(tmp_path):
+    """--bvh device: the BVH rebuilt by rt_bvh_build is the host builder's, so the files are equal."""
+    outs = []
+    for mode in ("host", "device"):
+        pfm = str(tmp_path / f"{mode}.pfm")
+        r = _run("--scene", os.path.join(ASSETS, "scenes", "suzanne.toml"), "--width", "80", "--height", "45", "--spp", "2",
+                 "--bounces", "4", "--pfm", pfm, "--bvh", mode)
+        assert r.returncode == 0, r.stderr
+        assert ("BVH built on the device" in r.stderr) == (mode == "device")
+        outs.append(open(pfm, "rb").read())
+    assert outs[0] == outs[1]
+    assert _run("--scene", HOUSE, "--bvh", "gpu").returncode == 2

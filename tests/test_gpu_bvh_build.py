@@ -100,3 +100,40 @@ def test_device_bvh_ten_million_triangles_under_half_a_second(rt, builder):
     built = builder.build(fresh)
     assert fresh.counts()["bvh_nodes"] == len(built["nodes"]) and fresh.bvh_depth == built["depth"]
     assert fresh.bvh_nodes_words().tobytes() == rt.Scene.synthetic_field(ASSETS, 3).bvh_nodes_words().tobytes()
+
+
+def _fuzz_scene(rt, rng):
+    """Mixed primitive soups: clustered, planar, duplicated and lattice-snapped triangles, spheres of
+    radius zero, axis-aligned and skewed planes."""
+    b = rt.SceneBuilder()
+    b.add_material((0.8, 0.8, 0.8), 1.0, 0.0)
+    for _ in range(int(rng.integers(0, 40))):
+        b.add_sphere(tuple(float(v) for v in rng.uniform(-6, 6, 3)), float(rng.choice([0.0, 0.1, 0.7])), 0)
+    for _ in range(int(rng.integers(0, 4))):
+        p = rng.uniform(-5, 5, 3)
+        b.add_plane(tuple(map(float, p)), tuple(map(float, rng.uniform(-3, 3, 3))), tuple(map(float, rng.uniform(-3, 3, 3))), 0)
+    count = int(rng.choice([0, 1, 7, 60, 700, 5000, 20000]))
+    if count:
+        kind = int(rng.integers(0, 4))
+        centers = rng.uniform(-8, 8, size=(count, 1, 3))
+        if kind == 1:      # a few tight clusters: deep, unbalanced trees
+            centers = rng.choice(rng.uniform(-8, 8, size=(5, 3)), size=count)[:, None, :] + rng.normal(0, 0.05, (count, 1, 3))
+        elif kind == 2:    # everything in one plane: zero extents, signed zeros
+            centers[:, :, 1] = 0.0
+        v = centers + rng.normal(0, 0.3, size=(count, 3, 3))
+        if kind == 2:
+            v[:, :, 1] = np.where(rng.random((count, 3)) < 0.5, 0.0, -0.0)
+        if kind == 3:      # lattice: exact ties of centroids and bounds, many duplicates
+            v = np.round(v * 2) / 2
+        v = v.reshape(-1, 3).astype(np.float32)
+        t = np.zeros((count, 6), np.uint32)
+        t[:, 0:3] = np.arange(count * 3, dtype=np.uint32).reshape(count, 3)
+        b.add_mesh_raw(v, np.array([[0, 1, 0]], np.float32), t, 0)
+    elif rng.random() < 0.5:
+        b.add_sphere((0.0, 0.0, 0.0), 1.0, 0)   # never an empty scene
+    return b
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("RT_BVH_FUZZ_SEEDS", "24"))))
+def test_device_bvh_fuzz(rt, builder, seed):
+    _check(rt, builder, _fuzz_scene(rt, np.random.default_rng(500 + seed)).build())
