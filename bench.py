@@ -22,6 +22,8 @@ value      = rays traced by all ranks (counted in-kernel by the timed kernels: c
              on the launch stream, max over ranks), inputs resident in HBM.
 e2e        = same metric through the public API with HOST buffers inside the timed region:
              scene + camera upload, render, reduce, device -> host read of the result.
+clocks     = SM clock / power / throttle reasons sampled through in-process NVML every 500 ms from
+             before the warm-up on; only samples inside the timed region are reported.
 roofline   = configs A, B, C, E are bound by instruction issue: algorithmic FP32
              operations of the step (counted exactly by the reference-order kernel, untimed;
              18 / 45 / 30 / 40 per node / triangle / sphere / plane test + 250 per shaded
@@ -29,7 +31,9 @@ roofline   = configs A, B, C, E are bound by instruction issue: al
              --fmad=false, so one operation is one issued instruction. Config D (scene beyond
              L2) gets the HBM roofline: algorithmic bytes (32 B per box test + 48 B per
              triangle test + the per-hit / per-bounce terms) per second against the measured
-             copy bandwidth, with the DRAM traffic ncu measured beside it.
+             copy bandwidth. `roofline.measured` / `roofline.traffic` carry what ncu counted over
+             every launch of the same step (profiles/measured.json, tools/ncu_step.py): warp and
+             thread instructions, the share of the issue slots they filled, DRAM bytes.
 cpu_baseline / --impl reference = the C++ oracle (a restatement of shader.wgsl; the Rust +
              wgpu reference cannot be built or run in this image) on all host cores, on a
              bounded sample of the same workload. kind = "port".
@@ -623,6 +627,10 @@ def main():
         hbm = {"bound": "hbm", "achieved": abytes / render_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                "frac": abytes / render_s / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
                "algorithmic_bytes_per_step": int(abytes), "render_ms": render_s * 1e3}
+        if cfg["name"] == "D":
+            hbm["note"] = ("achieved counts ALGORITHMIC bytes (SURVEY §8d), most of which L1 / L2 serve; `traffic` is "
+                           "the DRAM traffic ncu measured for the step. The deep walk is bound by divergence and "
+                           "dependent-load latency (11.4 of 32 lanes), not by bandwidth (DESIGN.md section 5)")
         measured = load_measured_profile(cfg["name"])
         if measured:
             m = dict(measured.get("issue") or {})

@@ -1438,29 +1438,36 @@ int rt_upload_scene(RtContext* ctx, const RtSceneDesc* s) {
         return fail(ctx, RT_ERR_INVALID_ARGUMENT,
                     "BVH depth %u exceeds the reference's 64-entry traversal stack", depth);
 
-    // ---- re-layout ----
-    std::vector<float4> nodes((size_t)s->bvh_node_count * 2);
-    for (uint32_t i = 0; i < s->bvh_node_count; i++) {
-        const RtBvhNode& n = s->bvh_nodes[i];
-        uint32_t meta = n.split_axis << 30;
-        if (n.primitives_len > 0) {
-            meta = n.primitives_len;
-            for (uint32_t k = 0; k < n.primitives_len; k++)
-                if (s->primitives[n.primitives_or_second_child_index + k].primitive_type != 2u)
-                    meta |= 0x20000000u;  // leaf holds a sphere or plane
+    // ---- re-layout (per-node and per-slot loops on all host threads: 10 M triangles are 2 GB of records) ----
+    rtf::RawFloat4Vec nodes;
+    nodes.resize((size_t)s->bvh_node_count * 2);
+    rtf::parallel_ranges(s->bvh_node_count, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            const RtBvhNode& n = s->bvh_nodes[i];
+            uint32_t meta = n.split_axis << 30;
+            if (n.primitives_len > 0) {
+                meta = n.primitives_len;
+                for (uint32_t k = 0; k < n.primitives_len; k++)
+                    if (s->primitives[n.primitives_or_second_child_index + k].primitive_type != 2u)
+                        meta |= 0x20000000u;  // leaf holds a sphere or plane
+            }
+            nodes[2 * i] = make_float4(n.min[0], n.min[1], n.min[2], bits(n.primitives_or_second_child_index));
+            nodes[2 * i + 1] = make_float4(n.max[0], n.max[1], n.max[2], bits(meta));
         }
-        nodes[2 * (size_t)i] = make_float4(n.min[0], n.min[1], n.min[2], bits(n.primitives_or_second_child_index));
-        nodes[2 * (size_t)i + 1] = make_float4(n.max[0], n.max[1], n.max[2], bits(meta));
-    }
+    });
 
     const uint32_t slots = s->primitive_count;
     const size_t rec_count = (size_t)slots + s->sphere_count + s->plane_count;
-    std::vector<float4> records(rec_count * 4, make_float4(0.f, 0.f, 0.f, 0.f));
-    std::vector<float4> tri_normals((size_t)slots * 3, make_float4(0.f, 0.f, 0.f, 0.f));
+    rtf::RawFloat4Vec records, tri_normals;
+    records.resize(rec_count * 4);
+    tri_normals.resize((size_t)slots * 3);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
     auto write_sphere = [&](size_t rec, const RtSphere& sp) {
         records[rec * 4 + 0] = make_float4(sp.pos[0], sp.pos[1], sp.pos[2], bits(0u));
         records[rec * 4 + 1] = make_float4(sp.radius, sp.radius * sp.radius, bits(sp.material_id), 0.f);
+        records[rec * 4 + 2] = zero4;
+        records[rec * 4 + 3] = zero4;
     };
     auto write_plane = [&](size_t rec, const RtPlane& pl) {
         records[rec * 4 + 0] = make_float4(pl.pos[0], pl.pos[1], pl.pos[2], bits(1u));
@@ -1468,46 +1475,59 @@ int rt_upload_scene(RtContext* ctx, const RtSceneDesc* s) {
         records[rec * 4 + 2] = make_float4(pl.base_change[0][0], pl.base_change[1][0], pl.base_change[2][0], 0.f);
         records[rec * 4 + 3] = make_float4(pl.base_change[0][2], pl.base_change[1][2], pl.base_change[2][2], 0.f);
     };
-    for (uint32_t slot = 0; slot < slots; slot++) {
-        const RtPrimitiveInfo& info = s->primitives[slot];
-        if (info.primitive_type == 0) {
-            if (info.index >= s->sphere_count)
-                return fail(ctx, RT_ERR_INVALID_ARGUMENT, "primitive %u: sphere index out of range", slot);
-            if (s->spheres[info.index].material_id >= s->material_count)
-                return fail(ctx, RT_ERR_INVALID_ARGUMENT, "sphere %u: material out of range", info.index);
-            write_sphere(slot, s->spheres[info.index]);
-        } else if (info.primitive_type == 1) {
-            if (info.index >= s->plane_count)
-                return fail(ctx, RT_ERR_INVALID_ARGUMENT, "primitive %u: plane index out of range", slot);
-            if (s->planes[info.index].material_id >= s->material_count)
-                return fail(ctx, RT_ERR_INVALID_ARGUMENT, "plane %u: material out of range", info.index);
-            write_plane(slot, s->planes[info.index]);
-        } else if (info.primitive_type == 2) {
-            if (info.index >= s->triangle_count)
-                return fail(ctx, RT_ERR_INVALID_ARGUMENT, "primitive %u: triangle index out of range", slot);
-            const RtTriangle& t = s->triangles[info.index];
-            if (t.vertex_0 >= s->vertex_count || t.vertex_1 >= s->vertex_count ||
-                t.vertex_2 >= s->vertex_count || t.normal_0 >= s->normal_count ||
-                t.normal_1 >= s->normal_count || t.normal_2 >= s->normal_count ||
-                t.material_id >= s->material_count)
-                return fail(ctx, RT_ERR_INVALID_ARGUMENT, "triangle %u: index out of range", info.index);
-            const RtVec3 &a = s->vertices[t.vertex_0], &b = s->vertices[t.vertex_1],
-                         &c = s->vertices[t.vertex_2];
-            // edge_0 = b - a, edge_1 = c - a (shader.wgsl:415-416): single f32 subtractions,
-            // so hoisting them to upload time leaves every bit unchanged.
-            records[(size_t)slot * 4 + 0] = make_float4(a.x, a.y, a.z, bits(2u));
-            records[(size_t)slot * 4 + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, bits(t.material_id));
-            records[(size_t)slot * 4 + 2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.f);
-            const RtVec3 &n0 = s->normals[t.normal_0], &n1 = s->normals[t.normal_1],
-                         &n2 = s->normals[t.normal_2];
-            tri_normals[(size_t)slot * 3 + 0] = make_float4(n0.x, n0.y, n0.z, 0.f);
-            tri_normals[(size_t)slot * 3 + 1] = make_float4(n1.x, n1.y, n1.z, 0.f);
-            tri_normals[(size_t)slot * 3 + 2] = make_float4(n2.x, n2.y, n2.z, 0.f);
-        } else {
-            return fail(ctx, RT_ERR_INVALID_ARGUMENT, "primitive %u: unknown type %u", slot,
-                        info.primitive_type);
+    // The first invalid primitive (lowest slot) is the one reported, whatever thread met it.
+    std::mutex bad_mutex;
+    size_t bad_slot = (size_t)-1;
+    std::string bad_text;
+    auto report = [&](size_t slot, const char* fmt, uint32_t a, uint32_t b = 0) {
+        char buf[160];
+        snprintf(buf, sizeof buf, fmt, a, b);
+        std::lock_guard<std::mutex> lock(bad_mutex);
+        if (slot < bad_slot) {
+            bad_slot = slot;
+            bad_text = buf;
         }
-    }
+    };
+    rtf::parallel_ranges(slots, [&](size_t lo, size_t hi) {
+        for (size_t slot = lo; slot < hi; slot++) {
+            const RtPrimitiveInfo& info = s->primitives[slot];
+            float4* nrm = &tri_normals[slot * 3];
+            nrm[0] = nrm[1] = nrm[2] = zero4;
+            if (info.primitive_type == 0) {
+                if (info.index >= s->sphere_count) return report(slot, "primitive %u: sphere index out of range", (uint32_t)slot);
+                if (s->spheres[info.index].material_id >= s->material_count)
+                    return report(slot, "sphere %u: material out of range", info.index);
+                write_sphere(slot, s->spheres[info.index]);
+            } else if (info.primitive_type == 1) {
+                if (info.index >= s->plane_count) return report(slot, "primitive %u: plane index out of range", (uint32_t)slot);
+                if (s->planes[info.index].material_id >= s->material_count)
+                    return report(slot, "plane %u: material out of range", info.index);
+                write_plane(slot, s->planes[info.index]);
+            } else if (info.primitive_type == 2) {
+                if (info.index >= s->triangle_count)
+                    return report(slot, "primitive %u: triangle index out of range", (uint32_t)slot);
+                const RtTriangle& t = s->triangles[info.index];
+                if (t.vertex_0 >= s->vertex_count || t.vertex_1 >= s->vertex_count || t.vertex_2 >= s->vertex_count ||
+                    t.normal_0 >= s->normal_count || t.normal_1 >= s->normal_count || t.normal_2 >= s->normal_count ||
+                    t.material_id >= s->material_count)
+                    return report(slot, "triangle %u: index out of range", info.index);
+                const RtVec3 &a = s->vertices[t.vertex_0], &b = s->vertices[t.vertex_1], &c = s->vertices[t.vertex_2];
+                // edge_0 = b - a, edge_1 = c - a (shader.wgsl:415-416): single f32 subtractions,
+                // so hoisting them to upload time leaves every bit unchanged.
+                records[slot * 4 + 0] = make_float4(a.x, a.y, a.z, bits(2u));
+                records[slot * 4 + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, bits(t.material_id));
+                records[slot * 4 + 2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.f);
+                records[slot * 4 + 3] = zero4;
+                const RtVec3 &n0 = s->normals[t.normal_0], &n1 = s->normals[t.normal_1], &n2 = s->normals[t.normal_2];
+                nrm[0] = make_float4(n0.x, n0.y, n0.z, 0.f);
+                nrm[1] = make_float4(n1.x, n1.y, n1.z, 0.f);
+                nrm[2] = make_float4(n2.x, n2.y, n2.z, 0.f);
+            } else {
+                return report(slot, "primitive %u: unknown type %u", (uint32_t)slot, info.primitive_type);
+            }
+        }
+    });
+    if (bad_slot != (size_t)-1) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "%s", bad_text.c_str());
     for (uint32_t i = 0; i < s->sphere_count; i++) write_sphere((size_t)slots + i, s->spheres[i]);
     for (uint32_t i = 0; i < s->plane_count; i++)
         write_plane((size_t)slots + s->sphere_count + i, s->planes[i]);
@@ -1532,7 +1552,7 @@ int rt_upload_scene(RtContext* ctx, const RtSceneDesc* s) {
         arena_need += alloc_bytes ? alloc_bytes : 16;
         return pieces.size() - 1;
     };
-    auto piece4 = [&](const std::vector<float4>& v, size_t extra = 0) {
+    auto piece4 = [&](const auto& v, size_t extra = 0) {
         return piece(v.data(), v.size() * sizeof(float4), (v.size() + extra) * sizeof(float4));
     };
     const size_t i_nodes = piece4(nodes), i_records = piece4(records), i_tri_normals = piece4(tri_normals);

@@ -5,6 +5,8 @@
 
 #include <cmath>
 #include <cstring>
+#include <memory>
+#include <thread>
 #include <vector>
 
 #include "rt_fast.cuh"
@@ -21,6 +23,40 @@ inline uint32_t word(float f) {
     uint32_t u;
     memcpy(&u, &f, 4);
     return u;
+}
+
+// std::vector whose resize() leaves new elements uninitialised: the big per-slot arrays are written
+// in full right after (by several threads), and zero-filling 0.5 GB first costs as much as filling it.
+template <typename T>
+struct DefaultInitAllocator : std::allocator<T> {
+    template <typename U>
+    struct rebind {
+        using other = DefaultInitAllocator<U>;
+    };
+    template <typename U, typename... Args>
+    void construct(U* p, Args&&... args) {
+        if constexpr (sizeof...(Args) == 0) ::new ((void*)p) U;
+        else ::new ((void*)p) U(static_cast<Args&&>(args)...);
+    }
+};
+using RawFloat4Vec = std::vector<float4, DefaultInitAllocator<float4>>;
+
+// fn(begin, end) over [0, n) cut into one contiguous range per host thread (large scenes: the
+// per-slot and per-node loops of the upload are independent per element).
+template <typename F>
+inline void parallel_ranges(size_t n, F fn) {
+    unsigned threads = std::thread::hardware_concurrency();
+    threads = threads < 1u ? 1u : (threads > 32u ? 32u : threads);
+    if (threads == 1u || n < ((size_t)1 << 16)) {
+        fn((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; t++) {
+        const size_t lo = n * t / threads, hi = n * (t + 1) / threads;
+        pool.emplace_back([=] { fn(lo, hi); });
+    }
+    for (auto& th : pool) th.join();
 }
 
 // ---- fast layout (rt_fast.cuh): N2 interior records, 48-byte triangle records, analytic
@@ -64,7 +100,8 @@ inline bool scene_has_loose_plane(const RtSceneDesc& s) {
 }
 
 struct FastLayout {
-    std::vector<float4> n2, tri, ana, pre, flat;
+    std::vector<float4> n2, ana, pre, flat;
+    RawFloat4Vec tri;
     std::vector<uint32_t> big_len, ana_paths;
     FastScene view{};
 };
@@ -121,6 +158,7 @@ inline void build_fast_layout(const RtSceneDesc& s, FastLayout& out) {
     bool any_big = false;
     std::vector<float4>& n2 = out.n2;
     n2.clear();
+    n2.reserve((size_t)(nodes / 2 + 1) * 4);  // one record per interior node at most
     // Iterative post-order over the reference tree (depth <= 64, but node counts reach 10^7).
     std::vector<Sub> result(nodes);
     {
@@ -184,23 +222,29 @@ inline void build_fast_layout(const RtSceneDesc& s, FastLayout& out) {
     // ---- triangle and analytic records ----
     out.ana.assign((size_t)(analytic ? analytic : 1) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
     std::vector<uint32_t> slot_of_analytic(analytic, kNone);
-    out.tri.assign((size_t)slots * kTriStride, make_float4(0.f, 0.f, 0.f, 0.f));
-    for (uint32_t slot = 0; slot < slots; slot++) {
-        const RtPrimitiveInfo& info = s.primitives[slot];
-        if (info.primitive_type == 2u) {
-            const RtTriangle& t = s.triangles[info.index];
-            const RtVec3 &a = s.vertices[t.vertex_0], &b = s.vertices[t.vertex_1], &c = s.vertices[t.vertex_2];
-            // edge_0 = b - a, edge_1 = c - a (shader.wgsl:415-416): single f32 subtractions,
-            // so hoisting them to upload time leaves every bit unchanged.
-            out.tri[(size_t)slot * kTriStride + 0] = make_float4(a.x, a.y, a.z, bits(2u));
-            out.tri[(size_t)slot * kTriStride + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, bits(t.material_id));
-            out.tri[(size_t)slot * kTriStride + 2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.f);
-        } else {
-            const uint32_t index = info.primitive_type == 0u ? info.index : s.sphere_count + info.index;
-            slot_of_analytic[index] = slot;
-            out.tri[(size_t)slot * kTriStride + 0] = make_float4(bits(index), 0.f, 0.f, bits(info.primitive_type));
+    out.tri.resize((size_t)slots * kTriStride);
+    parallel_ranges(slots, [&](size_t lo, size_t hi) {
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (size_t slot = lo; slot < hi; slot++) {
+            const RtPrimitiveInfo& info = s.primitives[slot];
+            float4* q = &out.tri[slot * kTriStride];
+            if (info.primitive_type == 2u) {
+                const RtTriangle& t = s.triangles[info.index];
+                const RtVec3 &a = s.vertices[t.vertex_0], &b = s.vertices[t.vertex_1], &c = s.vertices[t.vertex_2];
+                // edge_0 = b - a, edge_1 = c - a (shader.wgsl:415-416): single f32 subtractions,
+                // so hoisting them to upload time leaves every bit unchanged.
+                q[0] = make_float4(a.x, a.y, a.z, bits(2u));
+                q[1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, bits(t.material_id));
+                q[2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.f);
+            } else {
+                const uint32_t index = info.primitive_type == 0u ? info.index : s.sphere_count + info.index;
+                slot_of_analytic[index] = (uint32_t)slot;  // an analytic primitive sits in exactly one slot
+                q[0] = make_float4(bits(index), 0.f, 0.f, bits(info.primitive_type));
+                q[1] = zero;
+                q[2] = zero;
+            }
         }
-    }
+    });
     for (uint32_t i = 0; i < s.sphere_count; i++) {
         const RtSphere& sp = s.spheres[i];
         float4* r = &out.ana[(size_t)i * 4];
