@@ -116,7 +116,7 @@ def load_scene(rt, cfg, bvh_device=None, info=None):
         if info is not None:
             info.update({"where": f"cuda:{bvh_device} (rt_bvh_build)", "device_ms": built["device_ms"],
                          "with_upload_download_ms": (time.perf_counter() - t0) * 1e3,
-                         "nodes": int(len(built["nodes"])), "depth": built["depth"]})
+                         "nodes": built["node_count"], "depth": built["depth"]})
         builder.close()
         return scene
     return rt.Scene.load_toml(os.path.join(ROOT, "assets", "scenes", f"{cfg['scene']}.toml"))

@@ -66,6 +66,11 @@ int rt_scene_bvh_input(const RtHostScene* s, RtBvhBuildInput* out);
 /* Installs a BVH built elsewhere (rt_bvh_build): flattened nodes, leaf-ordered primitives, depth. */
 int rt_scene_set_bvh(RtHostScene* s, const RtBvhNode* nodes, uint32_t node_count,
                      const RtPrimitiveInfo* primitives, uint32_t primitive_count, uint32_t depth);
+/* The same without the intermediate copy: rt_scene_bvh_storage sizes the scene's own node and
+ * primitive arrays (primitive count = spheres + planes + triangles) and returns where to write them
+ * — pass the pointers to rt_bvh_build_fetch — and rt_scene_bvh_commit records the depth. */
+int rt_scene_bvh_storage(RtHostScene* s, uint32_t node_count, RtBvhNode** nodes, RtPrimitiveInfo** primitives);
+int rt_scene_bvh_commit(RtHostScene* s, uint32_t depth);
 /* (Re)builds the BVH with the host builder (what rt_scene_finalize does). */
 int rt_scene_build_bvh(RtHostScene* s, char* err, size_t err_len);
 

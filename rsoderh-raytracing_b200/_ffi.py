@@ -129,6 +129,8 @@ HOST_SIGNATURES = {
     "rt_scene_bvh_input": (C.c_int, [_vp, C.POINTER(RtBvhBuildInput)]),
     "rt_scene_set_bvh": (C.c_int, [_vp, _vp, _u32, _vp, _u32, _u32]),
     "rt_scene_build_bvh": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
+    "rt_scene_bvh_storage": (C.c_int, [_vp, _u32, C.POINTER(_vp), C.POINTER(_vp)]),
+    "rt_scene_bvh_commit": (C.c_int, [_vp, _u32]),
     "rt_scene_free": (None, [_vp]),
     "rt_scene_desc": (C.c_int, [_vp, C.POINTER(RtSceneDesc)]),
     "rt_scene_camera": (C.c_int, [_vp, _f3, _f3, _f3, _f3]),

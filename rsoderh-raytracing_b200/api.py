@@ -237,18 +237,24 @@ class DeviceBvhBuilder:
         t0 = time.perf_counter()
         self._check(self._lib.rt_bvh_build(self._ctx, C.byref(inp), C.byref(node_count), C.byref(depth), C.byref(ms)))
         t1 = time.perf_counter()
-        nodes = np.empty((node_count.value, 12), dtype=np.uint32)
-        primitives = np.empty((prims, 2), dtype=np.uint32)
-        self._check(self._lib.rt_bvh_build_fetch(self._ctx, nodes.ctypes.data, primitives.ctypes.data))
-        t2 = time.perf_counter()
         if install:
-            st = _ffi.host_lib().rt_scene_set_bvh(scene._handle, nodes.ctypes.data, node_count.value,
-                                                  primitives.ctypes.data, prims, depth.value)
+            # straight into the scene's own arrays: one pass over the memory
+            nodes_ptr, prims_ptr = C.c_void_p(), C.c_void_p()
+            st = _ffi.host_lib().rt_scene_bvh_storage(scene._handle, node_count.value, C.byref(nodes_ptr), C.byref(prims_ptr))
             if st:
-                raise RtError(st, "rt_scene_set_bvh refused the device-built BVH")
+                raise RtError(st, "rt_scene_bvh_storage refused the device-built BVH")
+            self._check(self._lib.rt_bvh_build_fetch(self._ctx, nodes_ptr, prims_ptr))
+            t2 = time.perf_counter()
+            _ffi.host_lib().rt_scene_bvh_commit(scene._handle, depth.value)
             scene.refresh()
-        return {"nodes": nodes, "primitives": primitives, "depth": int(depth.value), "device_ms": float(ms.value),
-                "build_call_ms": (t1 - t0) * 1e3, "fetch_ms": (t2 - t1) * 1e3,
+            nodes = primitives = None
+        else:
+            nodes = np.empty((node_count.value, 12), dtype=np.uint32)
+            primitives = np.empty((prims, 2), dtype=np.uint32)
+            self._check(self._lib.rt_bvh_build_fetch(self._ctx, nodes.ctypes.data, primitives.ctypes.data))
+            t2 = time.perf_counter()
+        return {"nodes": nodes, "primitives": primitives, "node_count": int(node_count.value), "depth": int(depth.value),
+                "device_ms": float(ms.value), "build_call_ms": (t1 - t0) * 1e3, "fetch_ms": (t2 - t1) * 1e3,
                 "install_ms": (time.perf_counter() - t2) * 1e3}
 
 

@@ -2106,11 +2106,6 @@ int rt_bvh_build(RtContext* ctx, const RtBvhBuildInput* in, uint32_t* node_count
     if ((in->sphere_count && !in->spheres) || (in->plane_count && !in->plane_bounds) ||
         (in->triangle_count && (!in->triangles || !in->vertices)))
         return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_bvh_build: missing input array");
-    for (uint32_t i = 0; i < in->triangle_count; i++) {
-        const RtTriangle& t = in->triangles[i];
-        if (t.vertex_0 >= in->vertex_count || t.vertex_1 >= in->vertex_count || t.vertex_2 >= in->vertex_count)
-            return fail(ctx, RT_ERR_INVALID_ARGUMENT, "triangle %u names a vertex out of range", i);
-    }
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     bvh_release_result(ctx);
     const uint32_t n = (uint32_t)total;
@@ -2150,7 +2145,7 @@ int rt_bvh_build(RtContext* ctx, const RtBvhBuildInput* in, uint32_t* node_count
         cudaEventRecord(ev0, st);
         cudaMemsetAsync(b.counters, 0, 4 * sizeof(uint32_t), st);
         rtb::init_records_kernel<<<grid(n, rtb::kThreads), rtb::kThreads, 0, st>>>(
-            b, d_spheres, in->sphere_count, d_plane_bounds, in->plane_count, d_vertices, d_triangles,
+            b, d_spheres, in->sphere_count, d_plane_bounds, in->plane_count, d_vertices, in->vertex_count, d_triangles,
             n <= rtb::kLeafMax ? 1u : 0u);
         rtb::acc_init_kernel<<<grid((size_t)rtb::kFields * rtb::kBuckets, 256), 256, 0, st>>>(b, 1u);
         rtb::bucket_kernel<true><<<grid(n, rtb::kThreads), rtb::kThreads, 0, st>>>(b, 0);
@@ -2158,6 +2153,10 @@ int rt_bvh_build(RtContext* ctx, const RtBvhBuildInput* in, uint32_t* node_count
         ctx->launches += 4;
         if (!check(cudaMemcpyAsync(host_counters, b.counters, sizeof host_counters, cudaMemcpyDeviceToHost, st), "counter read")) break;
         if (!check(cudaStreamSynchronize(st), "bvh root pass")) break;
+        if (host_counters[2] & rtb::kErrBadIndex) {  // checked by init_records_kernel
+            status = fail(ctx, RT_ERR_INVALID_ARGUMENT, "a triangle names a vertex out of range");
+            break;
+        }
         level_start.push_back(0u);
         level_start.push_back(1u);
         int cur = 0, act = 0;

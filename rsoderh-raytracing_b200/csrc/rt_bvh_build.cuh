@@ -10,7 +10,7 @@
 //     order-free; the sign of a zero never reaches a comparison or a cost), so the nodes of one
 //     tree level are evaluated together, one pass over all primitives per level;
 //   * the swap loop is a fixed permutation of its input with a closed form (partition_dest
-//     below; tests/test_bvh_partition.py checks it against the literal loop): it needs one
+//     below; tests/test_bvh_levels.py checks it against the literal loop): it needs one
 //     prefix count of the "stays left" flags and two small scatter tables, all parallel;
 //   * node indices are pre-order positions, which follow from subtree sizes: the tree is built
 //     in creation order, then sizes go bottom-up and positions top-down, level by level.
@@ -40,7 +40,7 @@ constexpr int kScanItems = 4;          // items per thread in the prefix kernels
 constexpr int kScanBlock = kThreads * kScanItems;
 constexpr float kMax = 3.40282347e+38f;  // Vec3::MAX / Vec3::MIN of Bounds3::identity (scene.rs:67-72)
 
-enum BuildError : uint32_t { kErrNanCost = 1u, kErrEmptySide = 2u, kErrNodeOverflow = 4u };
+enum BuildError : uint32_t { kErrNanCost = 1u, kErrEmptySide = 2u, kErrNodeOverflow = 4u, kErrBadIndex = 8u };
 
 // f32::min / f32::max without NaNs (the first argument stays on ties, -0.0 == +0.0 included).
 __device__ __forceinline__ float min_rs(float a, float b) { return b < a ? b : a; }
@@ -85,8 +85,8 @@ __device__ __forceinline__ int* acc_at(const Build& b, int field, int bucket, ui
 // PrimitiveInfo::build_array (bvh.rs:40-72): spheres, planes, triangles, with their bounds
 // (scene.rs:173-180, 203-207, mesh.rs:143-147).
 __global__ void init_records_kernel(Build b, const RtSphere* spheres, uint32_t sphere_count, const float* plane_bounds,
-                                    uint32_t plane_count, const RtVec3* vertices, const RtTriangle* triangles,
-                                    uint32_t root_is_leaf) {
+                                    uint32_t plane_count, const RtVec3* vertices, uint32_t vertex_count,
+                                    const RtTriangle* triangles, uint32_t root_is_leaf) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= b.n) return;
     float lo[3], hi[3];
@@ -109,7 +109,11 @@ __global__ void init_records_kernel(Build b, const RtSphere* spheres, uint32_t s
     } else {
         index = p - sphere_count - plane_count;
         const RtTriangle t = triangles[index];
-        const uint32_t vi[3] = {t.vertex_0, t.vertex_1, t.vertex_2};
+        uint32_t vi[3] = {t.vertex_0, t.vertex_1, t.vertex_2};
+        if (vi[0] >= vertex_count || vi[1] >= vertex_count || vi[2] >= vertex_count) {
+            atomicOr(&b.counters[2], (uint32_t)kErrBadIndex);  // the build fails; stay in bounds
+            vi[0] = vi[1] = vi[2] = 0u;
+        }
         for (int k = 0; k < 3; k++) {
             lo[k] = kMax;
             hi[k] = -kMax;

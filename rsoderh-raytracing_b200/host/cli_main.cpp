@@ -158,11 +158,10 @@ int main(int argc, char** argv) {
         rt_scene_bvh_input(scene, &input);
         if (rt_bvh_build(builder, &input, &node_count, &depth, &device_ms) != RT_OK)
             return die("device BVH build failed", rt_last_error(builder));
-        const uint32_t prims = input.sphere_count + input.plane_count + input.triangle_count;
-        std::vector<RtBvhNode> nodes(node_count);
-        std::vector<RtPrimitiveInfo> primitives(prims);
-        if (rt_bvh_build_fetch(builder, nodes.data(), primitives.data()) != RT_OK ||
-            rt_scene_set_bvh(scene, nodes.data(), node_count, primitives.data(), prims, depth) != RT_OK)
+        RtBvhNode* nodes = nullptr;
+        RtPrimitiveInfo* primitives = nullptr;
+        if (rt_scene_bvh_storage(scene, node_count, &nodes, &primitives) != RT_OK ||
+            rt_bvh_build_fetch(builder, nodes, primitives) != RT_OK || rt_scene_bvh_commit(scene, depth) != RT_OK)
             return die("device BVH build failed", rt_last_error(builder));
         std::fprintf(stderr, "BVH built on the device in %.2f ms\n", device_ms);
         rt_destroy(builder);

@@ -210,6 +210,28 @@ int rt_scene_set_bvh(RtHostScene* s, const RtBvhNode* nodes, uint32_t node_count
     return RT_OK;
 }
 
+int rt_scene_bvh_storage(RtHostScene* s, uint32_t node_count, RtBvhNode** nodes, RtPrimitiveInfo** primitives) {
+    if (!s || !nodes || !primitives || node_count == 0) return RT_ERR_INVALID_ARGUMENT;
+    if (!s->scene.finalized) return RT_ERR_STATE;
+    rt::HostScene& h = s->scene;
+    const size_t prims = h.u_spheres.size() + h.u_planes.size() + h.u_triangles.size();
+    // The vectors are sized here and filled by the caller (rt_bvh_build_fetch copies straight into
+    // them): one pass over the memory instead of a download into a temporary plus a copy.
+    h.u_nodes.resize(node_count);
+    h.u_primitives.resize(prims);
+    h.bvh_depth = 0;
+    *nodes = h.u_nodes.data();
+    *primitives = h.u_primitives.data();
+    return RT_OK;
+}
+
+int rt_scene_bvh_commit(RtHostScene* s, uint32_t depth) {
+    if (!s) return RT_ERR_INVALID_ARGUMENT;
+    if (!s->scene.finalized || s->scene.u_nodes.empty()) return RT_ERR_STATE;
+    s->scene.bvh_depth = depth;
+    return RT_OK;
+}
+
 int rt_scene_build_bvh(RtHostScene* s, char* err, size_t err_len) {
     if (!s) return RT_ERR_INVALID_ARGUMENT;
     if (!s->scene.finalized) return RT_ERR_STATE;

@@ -20,4 +20,4 @@ if not os.environ.get("QB_NO_WARMUP"):
 out = b.build(scene)
 print(f"grid {grid}: {scene.counts()['triangles']} triangles generated in {t1 - t0:.2f} s; device build {out['device_ms']:.2f} ms, "
       f"call {out['build_call_ms']:.1f} ms, fetch {out['fetch_ms']:.1f} ms, install {out['install_ms']:.1f} ms; "
-      f"{len(out['nodes'])} nodes, depth {out['depth']}")
+      f"{out['node_count']} nodes, depth {out['depth']}")
