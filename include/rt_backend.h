@@ -146,8 +146,11 @@ int rt_get_profile(RtContext* ctx, RtWaveProfile* out);
  * keep the per-pixel addition order of shader.wgsl:1367-1371 (16 B per pixel and staged
  * sample; default at most 8 GiB, and never more than 3/4 of what the device has free when
  * rt_render runs). rt_set_memory_budget lowers (or raises) the two knobs; 0 keeps a value.
- * Measured on house.toml 1080p, 256 spp: 8 GiB staging 7.85 Grays/s, 2 GiB 7.66, 1 GiB 7.55;
- * 4 Mi slots 7.52, 2 Mi 7.19. rt_get_memory_usage reports what is allocated right now. */
+ * Measured on house.toml 1080p, 256 spp: 8 GiB staging 7.90 Grays/s, 4 GiB 7.88, 2 GiB 7.82
+ * (-1.0 %), 1 GiB 7.72 (-2.3 %), 512 MiB 7.52; 4 Mi slots 7.65, 2 Mi 7.28 — so 2 GiB + 8 Mi slots
+ * (3.4 GB) or 1 GiB + 8 Mi slots (2.4 GB) are the settings for a GPU that is shared. Renders that
+ * bring fewer than three paths per slot use a smaller part of the pool on their own.
+ * rt_get_memory_usage reports what is allocated right now. */
 int rt_set_memory_budget(RtContext* ctx, uint64_t staging_bytes, uint32_t path_slots);
 int rt_get_memory_usage(RtContext* ctx, uint64_t* bytes);
 

@@ -866,7 +866,13 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
     if (batch > sample_count) batch = sample_count;
     if (batch < 1) batch = 1;
     const uint64_t paths_per_batch = (uint64_t)base.pixel_ids * batch;
-    const uint32_t total_slots = (uint32_t)(paths_per_batch < ctx->wave_max_slots ? paths_per_batch : ctx->wave_max_slots);
+    // A slot should carry about three paths or more over the render: with fewer, most of the render is
+    // the pipeline filling and draining (measured: 640x360 x 64 spp 5.97 -> 5.80 ms, 1080p x 4 spp
+    // 5.11 -> 4.79 ms with half the slots; large renders keep the full pool).
+    uint64_t want_slots = paths_per_batch / 3u;
+    want_slots = (want_slots + 65535u) & ~(uint64_t)65535u;
+    if (want_slots < 262144u) want_slots = paths_per_batch < 262144u ? paths_per_batch : 262144u;
+    const uint32_t total_slots = (uint32_t)(want_slots < ctx->wave_max_slots ? want_slots : ctx->wave_max_slots);
     const int groups = total_slots >= 262144u ? ctx->wave_groups : 1;  // small frames: one group
     const uint32_t per_group = (total_slots + (uint32_t)groups - 1u) / (uint32_t)groups;
     int st = wave_reserve(ctx, per_group, groups, pixels * sizeof(float4) * (size_t)batch);
