@@ -377,8 +377,12 @@ def main():
     bvh_info = {}
     scene = load_scene(rt, cfg, bvh_device=local_rank, info=bvh_info)
     build_s = time.perf_counter() - t_build
-    env = rt.EnvironmentMaps([rt.Environment.synthetic(2048, 1024)])
+    t_env = time.perf_counter()
+    env = rt.EnvironmentMaps([rt.Environment.synthetic(2048, 1024)])   # HDRI texels + alias table (environments.rs:97-186)
+    env_s = time.perf_counter() - t_env
+    t_state = time.perf_counter()
     state = rt.State(scene, env, width, height, device=local_rank, max_bounces=BOUNCES)
+    state_s = time.perf_counter() - t_state   # State::new: context, scene re-layout + upload, environment upload
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
@@ -651,6 +655,7 @@ def main():
             "config": dict({"workload": cfg["workload"], "config": cfg["name"],
                             "l2": "256 MiB flush write between timed steps",
                             "rays_per_step": int(rays_per_step), "scene_build_s": build_s,
+                            "environment_build_s": env_s, "state_new_s": state_s,
                             **({"bvh_build": bvh_info} if bvh_info else {})}, **extra_config),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": hbm if cfg["name"] == "D" else issue,
