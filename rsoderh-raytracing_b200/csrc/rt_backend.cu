@@ -1792,6 +1792,7 @@ int rt_render(RtContext* ctx, uint32_t sample_begin, uint32_t sample_count, uint
         p.sample_count = sample_count;
         p.max_bounces = max_bounces;
         p.sphere_count = ctx->scene.sphere_count;
+        p.row_begin = 0u;
         dim3 grid((p.width + rtf::kFastTileW - 1) / rtf::kFastTileW, (p.height + rtf::kFastTileH - 1) / rtf::kFastTileH);
         rtf::render_fast_kernel<<<grid, rtf::kFastThreads, 0, ctx->stream>>>(p);
         e2 = cudaGetLastError();
@@ -1862,10 +1863,40 @@ int rt_first_hit(RtContext* ctx, uint32_t sample_index, uint32_t* slot_out, floa
         fp.height = ctx->height;
         fp.sample_begin = sample_index;
         fp.sphere_count = ctx->scene.sphere_count;
-        dim3 grid((fp.width + rtf::kFastTileW - 1) / rtf::kFastTileW,
-                  (fp.height + rtf::kFastTileH - 1) / rtf::kFastTileH);
-        rtf::first_hit_fast_kernel<<<grid, rtf::kFastThreads, 0, ctx->stream>>>(fp);
-        e = cudaGetLastError();
+        // Large frames go in four bands of rows: the device -> host copies of a band's maps run on a
+        // second stream while the next band is traced (the call is copy-bound: 8 bytes per pixel
+        // over PCIe against 0.05 ns of kernel time per pixel).
+        const uint32_t bands = count >= ((size_t)1 << 21) ? 4u : 1u;
+        const uint32_t band_rows = (((fp.height + bands - 1u) / bands) + (uint32_t)rtf::kFastTileH - 1u) /
+                                   (uint32_t)rtf::kFastTileH * (uint32_t)rtf::kFastTileH;
+        cudaStream_t copy_stream = ctx->wave_streams[0];
+        for (uint32_t band = 0; band < bands && e == cudaSuccess; band++) {
+            const uint32_t row0 = band * band_rows;
+            if (row0 >= fp.height) break;
+            const uint32_t rows = fp.height - row0 < band_rows ? fp.height - row0 : band_rows;
+            fp.row_begin = row0;
+            dim3 grid((fp.width + rtf::kFastTileW - 1) / rtf::kFastTileW, (rows + rtf::kFastTileH - 1) / rtf::kFastTileH);
+            rtf::first_hit_fast_kernel<<<grid, rtf::kFastThreads, 0, ctx->stream>>>(fp);
+            e = cudaGetLastError();
+            ctx->launches++;
+            if (bands > 1u && e == cudaSuccess) {
+                const size_t at = (size_t)row0 * fp.width, n = (size_t)rows * fp.width;
+                e = cudaEventRecord(ctx->wave_phase[band % RtContext::kMaxGroups], ctx->stream);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(copy_stream, ctx->wave_phase[band % RtContext::kMaxGroups], 0);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(slot_out + at, d_slot + at, n * 4, cudaMemcpyDeviceToHost, copy_stream);
+                if (e == cudaSuccess && t_out) e = cudaMemcpyAsync(t_out + at, d_t + at, n * 4, cudaMemcpyDeviceToHost, copy_stream);
+            }
+        }
+        ctx->launches--;  // counted once more below
+        if (bands > 1u) {
+            cudaEventRecord(ctx->ev_stop, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(copy_stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e == cudaSuccess) cudaEventElapsedTime(&ctx->first_hit_kernel_ms, ctx->ev_start, ctx->ev_stop);
+            ctx->launches++;
+            if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "first-hit pass failed: %s", cudaGetErrorString(e));
+            return RT_OK;
+        }
     } else {
         e = ctx->detailed ? launch_first_hit<true>(p, ctx->bvh_depth, ctx->stream)
                           : launch_first_hit<false>(p, ctx->bvh_depth, ctx->stream);

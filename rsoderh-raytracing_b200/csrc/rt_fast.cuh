@@ -533,6 +533,7 @@ struct FastParams {
     uint32_t sample_begin, sample_count;
     uint32_t max_bounces;
     uint32_t sphere_count;
+    uint32_t row_begin;  // first-hit kernel only: first image row of this launch's band
 };
 
 constexpr int kFastTileW = 16, kFastTileH = 8, kFastThreads = kFastTileW * kFastTileH;
@@ -787,6 +788,7 @@ __global__ void __launch_bounds__(kFastThreads) first_hit_fast_kernel(const Fast
     stage_pre(p.scene, spre);
     uint32_t px, py;
     fast_thread_pixel(px, py);
+    py += p.row_begin;
     uint32_t n = 0;
     if (px < p.width && py < p.height) {
         uint2 stack[kStackCap];
