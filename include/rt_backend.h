@@ -93,7 +93,9 @@ int rt_render(RtContext* ctx, uint32_t sample_begin, uint32_t sample_count, uint
  * closest hit of cast_ray for the camera ray of sample `sample_index`;
  * RT_MISS_SLOT on a miss; 0x80000000 | type << 28 | index for hits found only by the
  * brute-force fallback (shader.wgsl:583-598). t_out (optional) = hit distance, 0 on miss.
- * Host output buffers; synchronous. */
+ * Host output buffers; synchronous. Frames of 2 Mi pixels and more are traced in four bands of
+ * rows whose maps travel to the host on a second stream while the next band is traced (page-locked
+ * output buffers, rt_host_alloc, let that overlap happen: 4K, 1.68 -> 1.35 ms per call). */
 int rt_first_hit(RtContext* ctx, uint32_t sample_index, uint32_t* slot_out, float* t_out);
 /* Device time (CUDA events) of the kernel of the last rt_first_hit call, without its copies. */
 float rt_first_hit_kernel_ms(const RtContext* ctx);

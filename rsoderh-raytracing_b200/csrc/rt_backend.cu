@@ -425,6 +425,7 @@ struct RtContext {
     // scene: every array below lives in one of two arenas. An upload fills the arena that is not in
     // use and the two swap on success, so re-uploading a scene of the same size allocates nothing
     // (no kernel-mode driver call on the per-frame path) and a failed upload leaves the old scene.
+    cudaEvent_t first_hit_events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // per band
     void* scene_arena[2] = {nullptr, nullptr};
     size_t scene_arena_bytes[2] = {0, 0};
     int scene_arena_cur = 0;
@@ -1399,6 +1400,8 @@ void rt_destroy(RtContext* ctx) {
     cudaFree(ctx->d_graph_launches);
     cudaFree(ctx->d_built_nodes);
     cudaFree(ctx->d_built_prims);
+    for (cudaEvent_t ev : ctx->first_hit_events)
+        if (ev) cudaEventDestroy(ev);
     cudaFree(ctx->wave_arena);
     cudaFree(ctx->local_arena);
     cudaFree(ctx->d_local_profile);
@@ -1870,29 +1873,40 @@ int rt_first_hit(RtContext* ctx, uint32_t sample_index, uint32_t* slot_out, floa
         const uint32_t band_rows = (((fp.height + bands - 1u) / bands) + (uint32_t)rtf::kFastTileH - 1u) /
                                    (uint32_t)rtf::kFastTileH * (uint32_t)rtf::kFastTileH;
         cudaStream_t copy_stream = ctx->wave_streams[0];
+        for (int i = 0; i < 8 && bands > 1u && e == cudaSuccess; i++)
+            if (!ctx->first_hit_events[i]) e = cudaEventCreate(&ctx->first_hit_events[i]);
+        uint32_t bands_run = 0;
         for (uint32_t band = 0; band < bands && e == cudaSuccess; band++) {
             const uint32_t row0 = band * band_rows;
             if (row0 >= fp.height) break;
             const uint32_t rows = fp.height - row0 < band_rows ? fp.height - row0 : band_rows;
             fp.row_begin = row0;
             dim3 grid((fp.width + rtf::kFastTileW - 1) / rtf::kFastTileW, (rows + rtf::kFastTileH - 1) / rtf::kFastTileH);
+            // every band's kernel between its own pair of events: the kernel time stays the kernels'
+            // alone even when the copies go to pageable memory and block this thread in between
+            if (bands > 1u) cudaEventRecord(ctx->first_hit_events[2u * band], ctx->stream);
             rtf::first_hit_fast_kernel<<<grid, rtf::kFastThreads, 0, ctx->stream>>>(fp);
             e = cudaGetLastError();
             ctx->launches++;
+            bands_run++;
             if (bands > 1u && e == cudaSuccess) {
                 const size_t at = (size_t)row0 * fp.width, n = (size_t)rows * fp.width;
-                e = cudaEventRecord(ctx->wave_phase[band % RtContext::kMaxGroups], ctx->stream);
-                if (e == cudaSuccess) e = cudaStreamWaitEvent(copy_stream, ctx->wave_phase[band % RtContext::kMaxGroups], 0);
+                e = cudaEventRecord(ctx->first_hit_events[2u * band + 1u], ctx->stream);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(copy_stream, ctx->first_hit_events[2u * band + 1u], 0);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(slot_out + at, d_slot + at, n * 4, cudaMemcpyDeviceToHost, copy_stream);
                 if (e == cudaSuccess && t_out) e = cudaMemcpyAsync(t_out + at, d_t + at, n * 4, cudaMemcpyDeviceToHost, copy_stream);
             }
         }
         ctx->launches--;  // counted once more below
         if (bands > 1u) {
-            cudaEventRecord(ctx->ev_stop, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(copy_stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            if (e == cudaSuccess) cudaEventElapsedTime(&ctx->first_hit_kernel_ms, ctx->ev_start, ctx->ev_stop);
+            ctx->first_hit_kernel_ms = 0.0f;
+            for (uint32_t band = 0; band < bands_run && e == cudaSuccess; band++) {
+                float ms = 0.0f;
+                cudaEventElapsedTime(&ms, ctx->first_hit_events[2u * band], ctx->first_hit_events[2u * band + 1u]);
+                ctx->first_hit_kernel_ms += ms;
+            }
             ctx->launches++;
             if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "first-hit pass failed: %s", cudaGetErrorString(e));
             return RT_OK;
