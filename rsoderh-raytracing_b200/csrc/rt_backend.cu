@@ -668,6 +668,19 @@ int wave_reserve(RtContext* ctx, uint32_t slots, int groups, size_t staging_byte
 // the loop going while any slot is live. One graph launch replaces ~1600 kernel launches and every
 // host synchronisation of the loop: rt_render returns at once, and the loop stops within one body
 // of the last path instead of running up to two 8-wave chunks empty.
+// Upper bound on the bodies one batch can run: a slot ends a path within max_bounces + 3 waves and takes
+// the next one at once, so after (paths per slot + 2) such rounds nothing can be live; twice that, plus
+// slack, only ever stops a loop that would not have ended.
+uint32_t wave_max_bodies(const rtw::WaveParams* p, int groups, int body_waves) {
+    const uint64_t slots = (uint64_t)p[0].slots * (uint64_t)groups;
+    const uint64_t rounds = (uint64_t)p[0].path_total / (slots ? slots : 1u) + 2u;
+    const uint64_t waves = 2u * rounds * ((uint64_t)p[0].max_bounces + 3u) + 64u;
+    const uint64_t bodies = waves / (uint64_t)body_waves + 2u;
+    if (const char* k = getenv("RT_WAVE_MAX_BODIES"))  // test hook: provoke the cut-off
+        if (atol(k) > 0) return (uint32_t)atol(k);
+    return bodies > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)bodies;
+}
+
 int wave_graph_build(RtContext* ctx, const rtw::WaveParams* p, int groups, const unsigned* blocks, bool shallow) {
     const int body_waves = ctx->wave_body_waves;
     std::string key;
@@ -676,6 +689,8 @@ int wave_graph_build(RtContext* ctx, const rtw::WaveParams* p, int groups, const
     key.push_back((char)groups);
     key.push_back((char)body_waves);
     key.push_back(shallow ? 1 : 0);
+    const uint32_t max_bodies = wave_max_bodies(p, groups, body_waves);
+    key.append((const char*)&max_bodies, sizeof max_bodies);
     if (ctx->wave_exec && key == ctx->wave_graph_key) return RT_OK;
     std::string shape;
     shape.append((const char*)blocks, sizeof(unsigned) * 4);
@@ -712,6 +727,7 @@ int wave_graph_build(RtContext* ctx, const rtw::WaveParams* p, int groups, const
             lc.groups = (uint32_t)groups;
             lc.body_kernels = (uint32_t)(groups * 4 * body_waves + 1);
             lc.launches = ctx->d_graph_launches;
+            lc.max_bodies = max_bodies;
             void* args[2] = {&ctx->wave_graph_handle, &lc};
             cudaKernelNodeParams kp;
             memset(&kp, 0, sizeof kp);
@@ -737,8 +753,8 @@ int wave_graph_build(RtContext* ctx, const rtw::WaveParams* p, int groups, const
     ctx->wave_graph = nullptr;
     ctx->wave_graph_key.clear();
     if (!ctx->d_graph_launches) {
-        RT_CUDA(ctx, cudaMalloc(&ctx->d_graph_launches, sizeof(unsigned long long)));
-        RT_CUDA(ctx, cudaMemset(ctx->d_graph_launches, 0, sizeof(unsigned long long)));
+        RT_CUDA(ctx, cudaMalloc(&ctx->d_graph_launches, 3 * sizeof(unsigned long long)));
+        RT_CUDA(ctx, cudaMemset(ctx->d_graph_launches, 0, 3 * sizeof(unsigned long long)));
     }
     cudaGraph_t graph = nullptr;
     RT_CUDA(ctx, cudaGraphCreate(&graph, 0));
@@ -789,6 +805,7 @@ int wave_graph_build(RtContext* ctx, const rtw::WaveParams* p, int groups, const
         lc.groups = (uint32_t)groups;
         lc.body_kernels = (uint32_t)(groups * 4 * body_waves + 1);
         lc.launches = ctx->d_graph_launches;
+        lc.max_bodies = max_bodies;
         void* args[2] = {&handle, &lc};
         cudaKernelNodeParams kp;
         memset(&kp, 0, sizeof kp);
@@ -981,6 +998,7 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
                 ce = cudaEventRecord(ctx->wave_fork, ctx->stream);
                 if (ce == cudaSuccess) ce = cudaStreamWaitEvent(loop_stream, ctx->wave_fork, 0);
             }
+            if (ce == cudaSuccess) ce = cudaMemsetAsync(ctx->d_graph_launches + 1, 0, sizeof(unsigned long long), loop_stream);
             if (ce == cudaSuccess) ce = cudaGraphLaunch(ctx->wave_exec, loop_stream);
             if (ce == cudaSuccess && loop_stream != ctx->stream) {
                 ce = cudaEventRecord(ctx->wave_join[0], loop_stream);
@@ -1113,6 +1131,17 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
         cudaEventDestroy(t_end);
     }
     return status;
+}
+
+// After a synchronisation: did a graph loop stop at its safety bound? (Never seen; a render that did
+// would be incomplete, so the caller is told.)
+int wave_loop_check(RtContext* ctx) {
+    if (!ctx->d_graph_launches) return RT_OK;
+    unsigned long long cut = 0;
+    RT_CUDA(ctx, cudaMemcpy(&cut, ctx->d_graph_launches + 2, sizeof cut, cudaMemcpyDeviceToHost));
+    if (!cut) return RT_OK;
+    RT_CUDA(ctx, cudaMemset(ctx->d_graph_launches + 2, 0, sizeof cut));
+    return fail(ctx, RT_ERR_STATE, "wave loop did not terminate within its bound; the render is incomplete");
 }
 
 // ---- persistent CTA-local wavefront (rt_local.cuh): one asynchronous launch per render ----
@@ -1947,7 +1976,7 @@ int rt_sync(RtContext* ctx) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return RT_OK;
+    return wave_loop_check(ctx);
 }
 
 int rt_read_accum(RtContext* ctx, float* rgba_out) {
@@ -1959,7 +1988,7 @@ int rt_read_accum(RtContext* ctx, float* rgba_out) {
                                  (size_t)ctx->width * ctx->height * sizeof(float4),
                                  cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return RT_OK;
+    return wave_loop_check(ctx);
 }
 
 int rt_write_accum(RtContext* ctx, const float* rgba_in) {

@@ -514,12 +514,20 @@ struct WaveLoopCtrl {
     const WaveCtrl* group[4];
     uint32_t groups;
     uint32_t body_kernels;              // kernels one body runs, this one included
-    unsigned long long* launches;       // running total, for rt_launch_count
+    unsigned long long* launches;       // [0] running total of kernels, for rt_launch_count;
+                                        // [1] bodies of the current launch (the host zeroes it before a launch);
+                                        // [2] set to 1 when a launch was cut off at `max_bodies`
+    uint32_t max_bodies;                // far above what the batch can need: a loop that does not end is
+                                        // stopped and reported (rt_sync) instead of hanging the device
 };
 __global__ void wave_continue_kernel(cudaGraphConditionalHandle handle, const WaveLoopCtrl l) {
     uint32_t live = 0u;
     for (uint32_t g = 0; g < l.groups; g++) live += l.group[g]->live;
-    *l.launches += l.body_kernels;
+    l.launches[0] += l.body_kernels;
+    if (++l.launches[1] >= l.max_bodies && live != 0u) {
+        l.launches[2] = 1ull;
+        live = 0u;
+    }
     cudaGraphSetConditional(handle, live != 0u ? 1u : 0u);
 }
 

@@ -281,3 +281,20 @@ def test_random_scene_fuzz(rt, orc, env_small, seed):
     slots, t = st.first_hit(seed)
     oslots, ot, _ = ora.first_hit(seed)
     assert np.array_equal(slots, oslots) and t.tobytes() == ot.tobytes(), (seed, scene.counts())
+
+
+def test_graph_loop_safety_bound_is_reported(rt, house, env_small, monkeypatch):
+    """The graph's WHILE loop carries an upper bound on its bodies (far above what a batch needs); a
+    loop cut off there makes rt_sync / rt_read_accum fail instead of returning a partial image."""
+    st = rt.State(house, env_small, 320, 180, max_bounces=8)
+    st.render_samples(4)
+    st.sync()                                   # a normal render stays far below its bound
+    monkeypatch.setenv("RT_WAVE_MAX_BODIES", "1")
+    st.render_samples(4)
+    with pytest.raises(rt.RtError, match="did not terminate"):
+        st.sync()
+    monkeypatch.delenv("RT_WAVE_MAX_BODIES")
+    st.reset()
+    st.render_samples(4)                        # the context keeps working
+    st.sync()
+    st.close()
