@@ -884,10 +884,11 @@ int wave_render(RtContext* ctx, const RtContext::Env& e, uint32_t sample_begin, 
     if (batch > sample_count) batch = sample_count;
     if (batch < 1) batch = 1;
     const uint64_t paths_per_batch = (uint64_t)base.pixel_ids * batch;
-    // A slot should carry about three paths or more over the render: with fewer, most of the render is
-    // the pipeline filling and draining (measured: 640x360 x 64 spp 5.97 -> 5.80 ms, 1080p x 4 spp
-    // 5.11 -> 4.79 ms with half the slots; large renders keep the full pool).
-    uint64_t want_slots = paths_per_batch / 3u;
+    // A slot should carry two to three paths or more over the render: with fewer, most of the render
+    // is the pipeline filling and draining. Measured at 1080p with the full pool / this rule: 1 spp
+    // 1.66 / 1.59 ms, 2 spp 2.81 / 2.72, 4 spp 5.11 / 4.81, 8 spp 9.31 / 9.08; 640x360 x 64 spp 5.97 /
+    // 5.86. Large renders keep the full pool.
+    uint64_t want_slots = paths_per_batch <= 12000000ull ? paths_per_batch / 2u : paths_per_batch / 3u;
     want_slots = (want_slots + 65535u) & ~(uint64_t)65535u;
     if (want_slots < 262144u) want_slots = paths_per_batch < 262144u ? paths_per_batch : 262144u;
     const uint32_t total_slots = (uint32_t)(want_slots < ctx->wave_max_slots ? want_slots : ctx->wave_max_slots);
