@@ -495,7 +495,8 @@ def main():
                 state.upload_scene(scene)
             state.update()
             render_and_reduce()
-            host_accum.copy_(accum, non_blocking=True)
+            if rank == 0:      # the step's result is the reduced image, and it lives on rank 0
+                host_accum.copy_(accum, non_blocking=True)
             stream.synchronize()
 
         sampler = make_sampler()
@@ -603,6 +604,9 @@ def main():
         e2e = {"value": rays_per_step * steps / (total_e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s",
                "h2d_bytes_per_step": (scene_bytes if upload_scene_per_step else 0) + 80,
                "d2h_bytes_per_step": pixels * 16, "ms_per_step": total_e2e_ms / steps}
+        if world > 1:
+            e2e["note"] = "every rank uploads scene and camera; the reduced image is read back on rank 0"
+
         if e2e_full_ms is not None:
             e2e["note"] = (f"the {scene_bytes / 1e6:.0f} MB scene is resident (uploaded once, as State::new does); a step "
                            f"uploads the camera uniform. With the scene upload and its re-layout inside the region: "
