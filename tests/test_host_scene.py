@@ -295,3 +295,37 @@ def test_parallel_bvh_build_is_byte_identical(rt, monkeypatch):
         assert scene.counts()["triangles"] > 150000
         dumps[threads] = (scene.bvh_nodes_words().tobytes(), scene.primitives_words().tobytes(), scene.bvh_depth)
     assert dumps["1"] == dumps["3"] == dumps["8"]
+
+
+def test_bvh_can_be_built_elsewhere_and_installed(rt):
+    """rt_scene_synthetic_field_ex(build_bvh = 0) + rt_scene_bvh_input + rt_scene_set_bvh /
+    rt_scene_bvh_storage + commit: the seams the device builder (rt_bvh_build) uses, on the CPU."""
+    import ctypes as C
+    lib = rt._ffi.host_lib()
+    built = rt.Scene.synthetic_field(ASSETS, 2)
+    bare = rt.Scene.synthetic_field(ASSETS, 2, build_bvh=False)
+    assert bare.counts()["bvh_nodes"] == 0 and bare.counts()["primitives"] == 0
+    assert bare.counts()["triangles"] == built.counts()["triangles"] == 4080
+    inp = bare.bvh_input()
+    assert (inp.sphere_count, inp.plane_count, inp.triangle_count) == (0, 1, 4080)
+    pb = bare.plane_bounds()          # Plane::bounds = box of pos and pos + forward + right (scene.rs:203-207)
+    assert pb.shape == (1, 6) and np.all(pb[0, :3] <= pb[0, 3:]) and pb[0, 1] == pb[0, 4] == 0.0
+    nodes, prims = built.bvh_nodes_words(), built.primitives_words()
+    # (a) copy in
+    st = lib.rt_scene_set_bvh(bare._handle, nodes.ctypes.data, len(nodes), prims.ctypes.data, len(prims), built.bvh_depth)
+    assert st == 0
+    bare.refresh()
+    assert bare.bvh_nodes_words().tobytes() == nodes.tobytes() and bare.bvh_depth == built.bvh_depth
+    assert lib.rt_scene_set_bvh(bare._handle, nodes.ctypes.data, len(nodes), prims.ctypes.data, len(prims) - 1, 3) != 0
+    # (b) write straight into the scene's own arrays
+    other = rt.Scene.synthetic_field(ASSETS, 2, build_bvh=False)
+    pn, pp = C.c_void_p(), C.c_void_p()
+    assert lib.rt_scene_bvh_storage(other._handle, len(nodes), C.byref(pn), C.byref(pp)) == 0
+    C.memmove(pn, nodes.ctypes.data, nodes.nbytes)
+    C.memmove(pp, prims.ctypes.data, prims.nbytes)
+    assert lib.rt_scene_bvh_commit(other._handle, built.bvh_depth) == 0
+    other.refresh()
+    assert other.primitives_words().tobytes() == prims.tobytes() and other.counts()["bvh_nodes"] == len(nodes)
+    # (c) and the host builder on request
+    other.build_bvh_host()
+    assert other.bvh_nodes_words().tobytes() == nodes.tobytes()
