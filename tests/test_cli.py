@@ -92,3 +92,31 @@ def test_device_built_bvh_renders_the_same_file(tmp_path):
         outs.append(open(pfm, "rb").read())
     assert outs[0] == outs[1]
     assert _run("--scene", HOUSE, "--bvh", "gpu").returncode == 2
+
+
+def _build_c_example(tmp_path):
+    exe = str(tmp_path / "render_minimal")
+    pkg = os.path.join(ROOT, "rsoderh-raytracing_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "render_minimal.c"), "-L" + pkg, "-lrt_host", "-lrt_backend",
+                        "-Wl,-rpath," + pkg, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_headers_are_plain_c_and_the_c_example_links(tmp_path, cuda_available):
+    """include/*.h compile as pedantic C99 and a plain C host links against the two libraries; without
+    a GPU the program stops at rt_create with the backend's message (no CPU path)."""
+    exe = _build_c_example(tmp_path)
+    if not cuda_available:
+        r = subprocess.run([exe, HOUSE, str(tmp_path / "o.png"), "64", "36", "2"], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU path" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_example_renders(tmp_path):
+    exe = _build_c_example(tmp_path)
+    out = str(tmp_path / "o.png")
+    r = subprocess.run([exe, HOUSE, out, "96", "54", "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "96x54, 3 spp" in r.stdout and open(out, "rb").read(8) == b"\x89PNG\r\n\x1a\n"
