@@ -369,7 +369,9 @@ __global__ void __launch_bounds__(kShadeThreads, RT_WAVE_SHADE_MIN_BLOCKS) wave_
 __global__ void __launch_bounds__(kFinishThreads, RT_WAVE_FINISH_MIN_BLOCKS) wave_finish_kernel(const WaveParams p) {
     const uint32_t P = p.wave & 1u;
     WaveCtrl* c = p.b.ctrl;
+#if !RT_FINISH_PREPASS
     uint32_t* rayq = p.b.rayq + (size_t)P * 2u * p.slots;
+#endif
     const float sin_half_fov = rt_sin(p.camera.fov_y / 2.0f);
     const size_t pixels = (size_t)p.width * p.height;
     uint32_t n_paths = 0, n_rays = 0;
