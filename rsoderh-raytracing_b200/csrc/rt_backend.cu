@@ -2,8 +2,11 @@
 //
 // Replaces the reference's device/pipeline layer (src/state.rs) and its compute shader
 // (src/shaders/shader.wgsl) with sm_100a CUDA. The render path is the wavefront pipeline of
-// rt_wave.cuh (four dense kernels per wave on two streams). This file holds the C ABI, the
-// uploads, and the kernels that are NOT the product path but cross-checks of it:
+// rt_wave.cuh (four dense kernels per wave for two overlapping slot groups, the wave loop one
+// CUDA graph with a WHILE node: wave_graph_build / wave_render below). This file holds the C ABI,
+// the uploads (two scene arenas, so a re-upload allocates nothing), the host side of the device
+// BVH build (rt_bvh_build; kernels in rt_bvh_build.cuh), the NCCL group, and the kernels that are
+// NOT the product path but cross-checks of it:
 // `render_kernel` / `first_hit_kernel` below walk the reference-layout arrays in the
 // reference's order, one thread per pixel, and count node / primitive tests exactly like the
 // CPU restatement the tests compare with (rt_set_detailed_counters; RT_KERNEL=pixel) — the

@@ -3,7 +3,8 @@
 // reconstruction, shade_hit), plus two kernels that are NOT the render path: `render_fast_kernel`
 // (RT_KERNEL=fast), a thread-per-pixel megakernel over the same code kept as a cross-check of the
 // wavefront kernels, and `first_hit_fast_kernel`, the primary-ray parity hook behind rt_first_hit.
-// The render path is rt_local.cuh (per-warp wavefront engines) / rt_wave.cuh (one launch per stage).
+// The render path is rt_wave.cuh (four dense kernels per wave inside one CUDA-graph loop);
+// rt_local.cuh (RT_KERNEL=local) is the persistent single-launch alternative, kept tested.
 //
 // Semantics follow /root/reference/src/shaders/shader.wgsl (cast_ray_bvh 469-564,
 // cast_ray 567-601, trace_ray 1213-1303, main 1305-1373); the arithmetic is
