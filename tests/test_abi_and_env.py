@@ -4,6 +4,7 @@ import os
 import re
 import struct
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -270,3 +271,22 @@ def test_wave_kernels_keep_their_state_in_registers(rt):
     assert frame("wave_walk_kernelILb1")[0] <= 32          # stack in shared memory: spills only
     assert frame("wave_walk_kernelILb0")[0] <= 512 + 32    # 64 x 8-byte stack entries + spills
     assert frame("wave_shade_kernel")[0] <= 64
+
+
+def test_rust_declarations_are_generated_from_the_headers():
+    """bindings/rust/src/rt_sys.rs is what tools/gen_rust_bindings.py writes from include/*.h today, and
+    it declares every function of both headers with one parameter per C parameter."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_bindings.py"), "--check"])
+    assert r.returncode == 0, "bindings/rust/src/rt_sys.rs is stale: run tools/gen_rust_bindings.py"
+    rust = open(os.path.join(ROOT, "bindings", "rust", "src", "rt_sys.rs")).read()
+    declared = dict(re.findall(r"pub fn (rt_\w+)\((.*?)\)", rust))
+    for header in ("rt_backend.h", "rt_host.h"):
+        text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", header)).read(), flags=re.S)
+        for name, args in re.findall(r"\b(rt_\w+)\s*\(([^;{]*?)\)\s*;", text):
+            assert name in declared, f"{name} is missing from rt_sys.rs"
+            want = 0 if args.strip() == "void" else args.count(",") + 1
+            got = 0 if not declared[name].strip() else declared[name].count(",") + 1
+            assert got == want, (name, declared[name])
+    for struct, size_fields in (("RtBvhNode", 8), ("RtSceneDesc", 16), ("RtCounters", 12)):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % struct, rust, flags=re.S).group(1)
+        assert body.count("pub ") == size_fields, struct
