@@ -62,9 +62,9 @@ impl B200State {
         let materials = storage_bytes(&scene.materials);
         let spheres = storage_bytes(&scene.spheres);
         let planes = storage_bytes(&scene.planes.iter().map(|p| p.to_uniform()).collect::<Vec<_>>());
-        let vertices = storage_bytes(&packed.vertices);
-        let normals = storage_bytes(&packed.normals);
-        let triangles = storage_bytes(&packed.triangles);
+        let vertices = storage_bytes(&packed.vertices());
+        let normals = storage_bytes(&packed.normals());
+        let triangles = storage_bytes(&packed.triangles());
         let primitive_bytes = storage_bytes(&primitives);
         let node_bytes = storage_bytes(&bvh_nodes);
         let desc = RtSceneDesc {
@@ -75,11 +75,11 @@ impl B200State {
             planes: planes.as_ptr() as *const RtPlane,
             plane_count: scene.planes.len() as u32,
             vertices: vertices.as_ptr() as *const RtVec3,
-            vertex_count: packed.vertices.len() as u32,
+            vertex_count: packed.vertices().len() as u32,
             normals: normals.as_ptr() as *const RtVec3,
-            normal_count: packed.normals.len() as u32,
+            normal_count: packed.normals().len() as u32,
             triangles: triangles.as_ptr() as *const RtTriangle,
-            triangle_count: packed.triangles.len() as u32,
+            triangle_count: packed.triangles().len() as u32,
             primitives: primitive_bytes.as_ptr() as *const RtPrimitiveInfo,
             primitive_count: primitives.len() as u32,
             bvh_nodes: node_bytes.as_ptr() as *const RtBvhNode,
